@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py - SMPL-regressed frames/s of the MAX-GRNet regression head on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the whole hot path (GRU temporal encoder -> 3-iteration HMR regressor ->
+rot6d->R -> SMPL blend shapes -> kinematic chain -> LBS of 6890 vertices -> joint regression ->
+Kinect-25 joints + weak-perspective projection + theta) over one batch of synthetic backbone
+features: BASELINE.json configs[1], 64 sequences x 16 frames PER GPU, full mesh output.
+Sequences are independent, so N GPUs run N shards with no data-path collective (weak scaling).
+
+Own arm (default): one JSON line with `value` (inputs resident in HBM, CUDA-graph replay, CUDA
+events per step, L2 flushed between steps, max over ranks), `e2e` (host pinned buffers -> H2D ->
+step -> D2H of every output, per step), `roofline` (LBS kernel: algorithmic bytes / measured
+kernel time vs MEASURED_PEAKS.json), per-stage timings, `cpu_baseline` (the CPU FP32 oracle on
+this box's cores, rank 0 at N=1), `clocks` (NVML samples during the timed region).
+
+Reference arm (`--impl reference`): the reference's own CPU FP32 path for the same config, i.e.
+the oracle restatement under oracle/ (the reference's model modules cannot be imported or
+installed here - SURVEY.md 8(c); its geometry/kp_utils/wrapper code is pinned by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "smpl_regressed_frames_per_sec"
+UNIT = "frames/s"
+
+# algorithmic figures per frame (DESIGN.md "Measurement")
+LBS_BYTES_PER_FRAME = 6890 * 3 * 4 * 2 + 24 * 12 * 4          # v_posed in + verts out + A  = 166 512
+LBS_BYTES_ONCE = 6890 * 24 * 4                                 # lbs_weights, once per launch
+JREG_BYTES_PER_FRAME = 6890 * 3 * 4 + 12                       # verts in + 1 joint out (thorax row)
+FLOPS_PER_FRAME = {"gru": 2 * 2 * 3 * 2048 * 2048, "regressor": 2 * (2048 * 1024 + 3 * (160 * 1024 + 1024 * 1024 + 157 * 1024)),
+                   "blend": 2 * 218 * 20670}
+OUT_BYTES_PER_FRAME = (6890 * 3 + 29 * 3 + 29 * 2 + 25 * 3 + 85 + 24 * 9) * 4    # verts, kp_3d, kp_2d, kinect25, theta, rotmat
+IN_BYTES_PER_FRAME = 2048 * 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--seqs-per-gpu", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--variant", choices=["sparse", "dense"], default="sparse",
+                    help="synthetic SMPL weights: SMPL-like sparse (<=4 skin weights / vertex) or fully dense")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--gather", choices=["none", "joints", "mesh"], default="none",
+                    help="NCCL all-gather of Kinect-25 joints (or joints+mesh) inside the timed step (N>1)")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_models(args, want_gpu: bool, want_oracle: bool):
+    from gaitb200 import synthetic
+    smpl_data = synthetic.make_smpl_data(seed=0, variant=args.variant)
+    mean = synthetic.make_mean_params()
+    reg_state = synthetic.make_regressor_state(seed=0, decoder_gain=0.3)
+    gru_state = synthetic.make_gru_state(seed=0)
+    head = oracle = None
+    if want_gpu:
+        from gaitb200.head import GaitHead
+        head = GaitHead(smpl_data, mean, reg_state, gru_state).cuda()
+    if want_oracle:
+        from oracle.head import GaitHeadOracle
+        oracle = GaitHeadOracle(smpl_data, mean, reg_state, gru_state)
+    return head, oracle
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def time_oracle(oracle, feats, budget_s: float, min_runs: int = 1, max_runs: int = 5):
+    """Best-of timing of the CPU oracle on `feats`; returns (frames/s, runs, seconds per run)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    frames = feats.shape[0] * feats.shape[1]
+    oracle(feats[:1])                                    # warm-up (thread pool, allocator)
+    best, runs, t_start = float("inf"), 0, time.perf_counter()
+    while runs < max_runs and (runs < min_runs or time.perf_counter() - t_start < budget_s):
+        t0 = time.perf_counter()
+        oracle(feats)
+        best = min(best, time.perf_counter() - t0)
+        runs += 1
+    return frames / best, runs, best
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    from gaitb200 import synthetic
+    _, oracle = make_models(args, want_gpu=False, want_oracle=True)
+    S, T = args.seqs_per_gpu, args.frames
+    feats = synthetic.make_features(S, T, seed=1234)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(min(args.warmup, 1)):
+        oracle(feats[: max(1, S // 8)])
+    steps = max(1, min(args.steps, 20))                  # each step is a full 64x16 pass (~1 s of CPU work)
+    times = []
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle(feats)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > 150:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    value = S * T / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} full passes of {S}x{T} frames, torch {torch.__version__} CPU FP32, "
+                                   f"{cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"BASELINE configs[1]: {args.seqs_per_gpu} sequences x {args.frames} frames per GPU, "
+                        "GRU(2048) + 3-iter HMR regressor + SMPL LBS, full 6890-vertex mesh + Kinect-25 output",
+            "seqs_per_gpu": args.seqs_per_gpu, "frames_per_seq": args.frames,
+            "global_frames_per_step": args.seqs_per_gpu * args.frames * world, "smpl_weights": args.variant,
+            "sharding": f"sequences x{world}, no data-path collective" + ("" if args.gather == "none" else f", final all-gather: {args.gather}"),
+            "l2": "256 MiB L2 flush between timed steps (outside the event pairs); step working set ~0.5 GB > 126 MB L2",
+            "cuda_graph": not args.no_graph}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """NVML samples of SM clock / throttle reasons for one GPU while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device_index: int, period_s: float = 0.004):
+        self.samples, self.reasons, self.period = [], set(), period_s
+        self.max_mhz, self.ok = None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = torch.cuda.get_device_properties(device_index).uuid
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1.0)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": getattr(self, "err", "no samples")}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args, rank: int, local_rank: int, world: int):
+    import torch.distributed as dist
+    from gaitb200 import _lib, synthetic
+    from gaitb200.sharding import gather_sequences
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); the product has no CPU path. "
+                         "Use --impl reference for the CPU oracle arm.")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    S, T = args.seqs_per_gpu, args.frames
+    F = S * T
+    peaks = load_peaks()
+    head, _ = make_models(args, want_gpu=True, want_oracle=False)
+    feats_host = synthetic.make_features(S, T, seed=1234 + rank).pin_memory()
+
+    if args.no_graph:
+        head.plan(S, T)
+        n0 = _lib.launch_count()
+        head.step()
+        launches_per_step = _lib.launch_count() - n0
+    else:
+        head.capture(S, T)
+        launches_per_step = head.launches_per_step
+    head.input.copy_(feats_host, non_blocking=True)
+    torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def flush_l2():
+        flush_buf.fill_(1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather():
+        if world > 1 and args.gather != "none":
+            o = head.outputs()
+            gather_sequences(o["kinect25"], S * world)
+            if args.gather == "mesh":
+                gather_sequences(o["verts"], S * world)
+
+    # ---- device-resident throughput: inputs already in HBM, per-step CUDA events, L2 flushed between steps
+    for _ in range(args.warmup):
+        flush_l2(); head.step(); gather()
+    barrier()
+    evs = []
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            head.step()
+            gather()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms_local = sum(step_ms)
+    t = torch.tensor([total_ms_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = F * world * args.steps / (total_ms / 1e3)
+
+    # ---- end to end through the public API: pinned host features -> H2D -> step -> D2H of every output
+    outs = head.outputs()
+    host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
+    h2d = feats_host.numel() * 4
+    d2h = sum(v.numel() * 4 for v in host_out.values())
+
+    def e2e_step():
+        head.input.copy_(feats_host, non_blocking=True)
+        head.step()
+        for k, v in head.outputs().items():
+            host_out[k].copy_(v, non_blocking=True)
+
+    for _ in range(max(3, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e2e_steps = max(5, args.steps // 4)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    barrier()
+    te = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item()) / e2e_steps
+    e2e_value = F * world / (e2e_ms / 1e3)
+
+    if rank != 0:
+        return
+    # ---- per-stage timings (eager launches, L2 flushed before each) and rooflines
+    stages = head.profile_stages(iters=10, flush=flush_l2)
+    lbs_ms = stages["lbs"]["ms"]
+    lbs_bytes = F * LBS_BYTES_PER_FRAME + LBS_BYTES_ONCE
+    lbs_gbs = lbs_bytes / (lbs_ms * 1e-3) / 1e9
+    roofline = {"kernel": "smpl_lbs_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_launch": lbs_bytes, "kernel_ms": lbs_ms}
+    jr_ms = stages["joint_regress"]["ms"]
+    jr_bytes = F * JREG_BYTES_PER_FRAME + 6890 * 4
+    stage_report = {}
+    for name, s in stages.items():
+        e = {"ms": round(s["ms"], 5), "launches": s["launches"]}
+        if name in FLOPS_PER_FRAME:
+            tf = FLOPS_PER_FRAME[name] * F / (s["ms"] * 1e-3) / 1e12
+            e.update({"bound": "tensor", "achieved_tflops_fp32_equiv": round(tf, 3),
+                      "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 5)})
+        stage_report[name] = e
+    stage_report["lbs"].update({"bound": "hbm", "achieved_gbs": round(lbs_gbs, 1), "frac": round(lbs_gbs / peaks["hbm_gbs"], 4)})
+    jr_gbs = jr_bytes / (jr_ms * 1e-3) / 1e9
+    stage_report["joint_regress"].update({"bound": "hbm", "achieved_gbs": round(jr_gbs, 1), "frac": round(jr_gbs / peaks["hbm_gbs"], 4)})
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        _, oracle = make_models(args, want_gpu=False, want_oracle=True)
+        cores = os.cpu_count() or 1
+        v, runs, sec = time_oracle(oracle, feats_host.clone(), args.cpu_baseline_seconds)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"best of {runs} full passes of {S}x{T} frames ({sec:.3f} s each), oracle/ torch "
+                                  f"{torch.__version__} CPU FP32, {cores} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "roofline": roofline,
+        "stages": stage_report,
+        "cpu_baseline": cpu_baseline,
+        "whole_step_hbm_frac": (F * (IN_BYTES_PER_FRAME + OUT_BYTES_PER_FRAME) / (ms_per_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
+        "wall_s_timed_region": t_wall,
+        "step_ms_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
+        "library": str(_lib.LIB_PATH.relative_to(ROOT)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        from gaitb200.sharding import init_from_env
+        init_from_env("nccl")
+    try:
+        run_b200(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,170 @@
+/* gaitb200.h - C ABI of the B200-native (sm_100a) regression head for MAX-GRNet.
+ *
+ * The reference (lisqzqng/Video-based-gait-analysis-for-dementia) is pure Python/PyTorch: it has
+ * no FFI, plugin or operator registry.  Its "interface" for the hot path is a set of nn.Module
+ * classes and free functions.  This header is the boundary a native backend for
+ * those classes binds: every entry point names the reference function (file:line under
+ * /root/reference, or the smplx==0.1.26 routine the reference calls) whose arithmetic it replaces.
+ * The Python mirror of the reference API (package gaitb200) binds these through ctypes; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, a stream handle.  No torch types, no exceptions, no allocation:
+ *     the caller passes outputs and workspaces.
+ *   - every pointer is a DEVICE pointer to FP32 (or int32 where said), row-major, 16-byte aligned
+ *     base unless noted; `ld*` arguments are row strides in elements.
+ *   - work is enqueued on `stream` (a cudaStream_t) and the call returns immediately;
+ *     calls are re-entrant per stream.
+ *   - return 0 on success, a negative GAIT_ERR_* otherwise; gait_last_error() gives detail.
+ *   - inputs are never written; in/out aliasing is not allowed unless stated.
+ */
+#ifndef GAITB200_H
+#define GAITB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAIT_ABI_VERSION 1
+
+#define GAIT_OK 0
+#define GAIT_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, bad stride/alignment) */
+#define GAIT_ERR_CUDA (-2)        /* a CUDA runtime call or kernel launch failed */
+#define GAIT_ERR_UNSUPPORTED (-3) /* shape outside what the kernels are written for */
+#define GAIT_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define GAIT_NUM_JOINTS 24        /* SMPL kinematic tree */
+#define GAIT_NUM_BETAS 10
+#define GAIT_POSE_BASIS 207       /* 23 * 9 */
+#define GAIT_BLEND_K 218          /* 207 pose-blend + 10 shape-blend + 1 (template) */
+#define GAIT_BLEND_LD 224         /* row stride of the packed blend operands (K padded, zero filled) */
+
+typedef void* gait_stream_t;      /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int gait_abi_version(void);
+const char* gait_error_string(int code);
+const char* gait_last_error(void);            /* thread-local detail of the last failure */
+/* sm count / compute capability of the current device; fails unless it is sm_100. */
+int gait_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+int64_t gait_launch_count(void);
+
+/* ---- geometry: lib/utils/geometry.py ---------------------------------------------------- */
+/* rot6d_to_rotmat geometry.py:395-410 (eps=1e-6) and rot6d_to_rotmat_spin :368-387 (eps=1e-12).
+ * 6-vector i (interleaved (3,2)) is read at x6 + (i / group) * in_group_stride + (i % group) * 6
+ * (group=1, stride=6 for a plain (n,6) array; 24/160 reads the regressor state in place) -> R (n,3,3). */
+int gait_rot6d_to_rotmat(const float* x6, int group, int64_t in_group_stride, float* R, int64_t n, float eps,
+                         gait_stream_t stream);
+/* rotmat_to_rot6d geometry.py:389-393. R (n,3,3) -> (n,6). */
+int gait_rotmat_to_rot6d(const float* R, float* x6, int64_t n, gait_stream_t stream);
+/* rotation_matrix_to_quaternion geometry.py:213-293. R (n,3,row_stride), row_stride 3 or 4 -> (n,4) wxyz. */
+int gait_rotmat_to_quaternion(const float* R, int row_stride, float* quat, int64_t n, float eps,
+                              gait_stream_t stream);
+/* quaternion_to_angle_axis geometry.py:159-210. (n,4) -> (n,3). */
+int gait_quaternion_to_axis_angle(const float* quat, float* aa, int64_t n, gait_stream_t stream);
+/* rotation_matrix_to_angle_axis geometry.py:68-97 (quaternion route, NaN -> 0).
+ * Rotation i is written to aa[(i / group) * out_group_stride + out_offset + (i % group) * 3]
+ * (group=1, out_group_stride=3, out_offset=0 for a plain (n,3) result; 24/85/3 packs theta). */
+int gait_rotmat_to_axis_angle(const float* R, int row_stride, float* aa, int64_t n, int group,
+                              int64_t out_group_stride, int out_offset, gait_stream_t stream);
+/* quat2mat geometry.py:38-65. (n,4) wxyz -> (n,3,3). */
+int gait_quat2mat(const float* quat, float* R, int64_t n, gait_stream_t stream);
+/* Rodrigues.  variant 0: smplx lbs.batch_rodrigues (I + sin K + (1-cos) K^2), used by
+ * SMPL.forward(pose2rot=True) (lib/utils/smooth_pose.py:72-76);  variant 1: geometry.py:23-35
+ * (half-angle quaternion -> quat2mat).  aa (n,3) -> R (n,3,3). */
+int gait_batch_rodrigues(const float* aa, float* R, int64_t n, int variant, gait_stream_t stream);
+/* convert_weak_perspective_to_perspective geometry.py:427-446: cam (n,3)=[s,tx,ty] -> (n,3). */
+int gait_weak_perspective_to_translation(const float* cam, float* trans, int64_t n, float focal_length,
+                                         float img_res, gait_stream_t stream);
+/* perspective_projection geometry.py:448-479.  points (b,j,3); rotation (b,3,3) or NULL (identity);
+ * translation (b,3); center (b,2) or NULL (zeros); out (b,j,2) = K[(R p + t)/z] / out_divisor. */
+int gait_perspective_projection(const float* points, const float* rotation, const float* translation,
+                                const float* center, float focal_length, float out_divisor, float* out,
+                                int64_t b, int j, gait_stream_t stream);
+
+/* ---- dense layer: torch.nn.Linear as used at spin.py:216-222,259-265 ---------------------- */
+/* C[m,n] = sum_k A[m,k] * W[n,k] + bias[n] + Cin[m,n]   (bias, Cin optional; Cin may alias C).
+ * FP32 result: SIMT FP32 or FP32-accurate split-TF32 tensor-core path, chosen by shape. */
+int gait_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                gait_stream_t stream);
+
+/* ---- GRU: torch.nn.GRU as used by TemporalEncoder / gait_feat_encoder.py:51-57,88 --------- */
+size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H);
+/* One layer, one direction.  x (S,T,I) with frame stride ldx; weights in torch layout
+ * (W_ih (3H,I), W_hh (3H,H), gate order r,z,n); h0 (S,H) or NULL (zeros).
+ * y  (S,T,.) frame stride ldy : raw GRU output h_t (written at y + (s*T+t)*ldy, H wide)
+ * out (S,T,.) frame stride ldout, optional: h_t + resid[s,t,:]  (resid frame stride ldres; the
+ *     TemporalEncoder residual); NULL to skip.
+ * hn (S,H) optional final hidden state.  reverse!=0 runs t = T-1..0. */
+int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* W_hh, const float* b_ih,
+                   const float* b_hh, const float* h0, float* y, int64_t ldy, const float* resid,
+                   int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T, int64_t I,
+                   int64_t H, int reverse, void* workspace, size_t workspace_bytes, gait_stream_t stream);
+
+/* F.relu between the GRU and the optional output Linear of TemporalEncoder. y may alias x. */
+int gait_relu(const float* x, float* y, int64_t n, gait_stream_t stream);
+
+/* ---- HMR iterative regressor: spin.py:244-265 -------------------------------------------- */
+/* state = [pose6d(144) | betas(10) | cam(3)] = 157 floats, stored with row stride 160.
+ * W1x (Dh,Din) = fc1.weight[:, :Din];  W1s (Dh,160) = fc1.weight[:, Din:] zero padded;
+ * W2 (Dh,Dh); Wd (157,Dh) = [decpose;decshape;deccam].weight; bd (157).
+ * init (1,160) broadcast when init_rows==1, else (F,160).  state_out (F,160). */
+size_t gait_hmr_workspace_bytes(int64_t F, int64_t Dh);
+int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const float* W1s, const float* b1,
+                       const float* W2, const float* b2, const float* Wd, const float* bd,
+                       const float* init, int64_t init_rows, int n_iter, float* state_out, int64_t F,
+                       int64_t Din, int64_t Dh, void* workspace, size_t workspace_bytes,
+                       gait_stream_t stream);
+
+/* ---- SMPL: smplx==0.1.26 lbs.py via lib/models/smpl.py:108-130 ---------------------------- */
+/* Shape-dependent rest joints + 24-joint kinematic chain (smplx lbs.batch_rigid_transform), one
+ * warp per frame, parent transforms exchanged by warp shuffle level by level.
+ * R (F,24,3,3); betas (F,10) frame stride ldb; J_template (24,3) = J_regressor.v_template;
+ * J_shapedirs (24,3,10) = J_regressor.shapedirs; parents int32[24] (parents[0] = -1).
+ * A (F,24,12): rows of the 3x4 skinning transform with the rest joint removed;
+ * J_posed (F,24,3); coef (F,GAIT_BLEND_LD) optional: [R[1:]-I (207) | betas (10) | 1 | 0..]. */
+int gait_smpl_pose_chain(const float* R, const float* betas, int64_t ldb, const float* J_template,
+                         const float* J_shapedirs, const int32_t* parents, float* A, float* J_posed,
+                         float* coef, int64_t F, gait_stream_t stream);
+/* Blend shapes (smplx lbs.blend_shapes + pose offsets): v_posed (F,3V) = coef (F,224) . basis_t^T,
+ * basis_t (3V,224) = [posedirs^T | shapedirs | v_template | 0]. */
+int gait_smpl_blend(const float* coef, const float* basis_t, float* v_posed, int64_t F, int64_t V3,
+                    gait_stream_t stream);
+/* Linear blend skinning (last two lines of smplx lbs): verts[f,v] = (sum_j W[v,j] A[f,j]) [v_posed;1].
+ * v_posed (F,V,3); A (F,24,12); lbs_weights (V,24); verts (F,V,3). */
+int gait_smpl_lbs(const float* v_posed, const float* A, const float* lbs_weights, float* verts, int64_t F,
+                  int64_t V, gait_stream_t stream);
+/* vertices2joints (smplx lbs; lib/models/smpl.py:113, pare.py:70-76, spin.py:279-282):
+ * out (F,Rj,3) = Jreg (Rj,V) . verts (F,V,3). */
+int gait_joint_regress(const float* verts, const float* Jreg, float* out, int64_t F, int64_t V, int Rj,
+                       gait_stream_t stream);
+/* Joint assembly (smplx VertexJointSelector + smpl.py:114-121) with optional projection
+ * (smpl.py:176-186 / geometry.py:412-425) and Kinect-25 gather (kp_utils.py:26-36).
+ * Virtual joint v: v<24 -> J_posed; 24<=v<24+n_landmarks -> verts[landmark[v-24]];
+ * else -> extra[v-24-n_landmarks] (extra (F,n_extra,3)).  joint_map int32[J] picks virtual joints.
+ * joints (F,J,3); kp2d (F,J,2) optional (needs cam (F,3), frame stride ldcam):
+ *   t = [tx, ty, 2 f/(res s + 1e-9)], kp2d = f (X+t).xy/(X+t).z / kp2d_divisor;
+ * gather int32[n_gather] + gathered (F,n_gather,3) optional (entry -1 writes zeros). */
+int gait_joints_assemble(const float* J_posed, const float* verts, int64_t V, const int32_t* landmarks,
+                         int n_landmarks, const float* extra, int n_extra, const int32_t* joint_map, int J,
+                         float* joints, const float* cam, int64_t ldcam, float focal_length, float img_res,
+                         float kp2d_divisor, float* kp2d, const int32_t* gather, int n_gather,
+                         float* gathered, int64_t F, gait_stream_t stream);
+/* convert_kps (kp_utils.py:26-36) as a device gather: dst (F,Jd,3)[f,k] = src (F,Js,3)[f,idx[k]],
+ * zeros where idx[k] < 0 (a destination joint the source layout lacks). */
+int gait_gather_joints(const float* src, int Js, const int32_t* idx, int Jd, float* dst, int64_t F,
+                       gait_stream_t stream);
+/* theta packing (spin.py:288, pare.py:79): theta (F,85) = [cam(3) | axis-angle(72) | betas(10)],
+ * axis-angle from R (F,24,3,3) by the geometry.py:68-97 route. */
+int gait_pack_theta(const float* R, const float* cam, int64_t ldcam, const float* betas, int64_t ldb,
+                    float* theta, int64_t F, gait_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAITB200_H */

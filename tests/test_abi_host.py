@@ -1,0 +1,140 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/gaitb200.h declares,
+argument validation works without a GPU (no compute is enqueued), the host mirror of the
+reference API has the reference's tables / state_dict keys, and the product refuses CPU input."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from gaitb200 import _lib, kp_utils, synthetic
+from gaitb200 import smpl as PS
+from oracle import kp_utils as OK
+from oracle import regressor as OR
+from oracle import smpl as OS
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not _lib.LIB_PATH.exists():
+        subprocess.run(["make", "-C", str(ROOT), "-j", "8"], check=True)
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = (ROOT / "include" / "gaitb200.h").read_text()
+    declared = sorted(set(re.findall(r"\b(gait_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in gaitb200.h but not exported"
+    assert set(declared) == set(_lib.EXPORTS), set(declared) ^ set(_lib.EXPORTS)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(declared) <= exported
+
+
+def test_library_is_sm100a_only(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_version_and_error_strings(lib):
+    assert lib.gait_abi_version() == 1
+    assert lib.gait_error_string(0) == b"ok"
+    assert b"invalid" in lib.gait_error_string(-1)
+    assert lib.gait_launch_count() >= 0
+
+
+def test_argument_validation_without_gpu(lib):
+    # empty problems succeed without touching the device
+    assert lib.gait_rot6d_to_rotmat(None, 1, 6, None, 0, 1e-6, None) == 0
+    assert lib.gait_smpl_lbs(None, None, None, None, 0, 6890, None) == 0
+    assert lib.gait_linear(None, 0, None, 0, None, None, 0, None, 0, 0, 16, 16, None) == 0
+    assert lib.gait_gru_layer(None, 0, None, None, None, None, None, None, 0, None, 0, None, 0, None,
+                              0, 16, 8, 8, 0, None, 0, None) == 0
+    # bad arguments are rejected before any launch
+    assert lib.gait_rot6d_to_rotmat(None, 1, 6, None, 4, 1e-6, None) == -1
+    assert b"null" in lib.gait_last_error()
+    assert lib.gait_rot6d_to_rotmat(None, 1, 6, None, -1, 1e-6, None) == -1
+    assert lib.gait_rotmat_to_quaternion(C.c_void_p(16), 5, C.c_void_p(16), 1, 1e-6, None) == -1
+    assert lib.gait_batch_rodrigues(C.c_void_p(16), C.c_void_p(16), 1, 7, None) == -1
+    assert lib.gait_smpl_lbs(C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 6891, None) == -1
+    assert lib.gait_smpl_lbs(C.c_void_p(20), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 6890, None) == -1
+    assert lib.gait_linear(C.c_void_p(16), 4, C.c_void_p(16), 8, None, None, 0, C.c_void_p(16), 8, 2, 8, 8, None) == -1
+    assert lib.gait_gru_workspace_bytes(64, 16, 2048) == (64 * 16 * 6144 + 64 * 6144) * 4
+    assert lib.gait_hmr_workspace_bytes(1024, 1024) == 3 * 1024 * 1024 * 4
+    n0 = lib.gait_launch_count()
+    assert lib.gait_gru_layer(C.c_void_p(16), 8, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), None,
+                              C.c_void_p(16), 8, None, 0, None, 0, None, 2, 3, 8, 8, 0, C.c_void_p(16), 8, None) == -4
+    assert lib.gait_launch_count() == n0
+
+
+def test_product_has_no_cpu_path(smpl_data):
+    from gaitb200 import geometry as G
+    with pytest.raises(_lib.GaitLibraryError):
+        G.rot6d_to_rotmat(torch.zeros(2, 6))
+    with pytest.raises(TypeError):
+        G.rot6d_to_rotmat(np.zeros((2, 6), np.float32))
+    with pytest.raises(TypeError):
+        G.rotation_matrix_to_quaternion([1, 2, 3])
+    with pytest.raises(ValueError):
+        G.quaternion_to_angle_axis(torch.zeros(2, 3))
+    smpl = PS.SMPL(smpl_data)
+    with pytest.raises(_lib.GaitLibraryError):
+        smpl(betas=torch.zeros(1, 10), body_pose=torch.eye(3).expand(1, 23, 3, 3),
+             global_orient=torch.eye(3).expand(1, 1, 3, 3), pose2rot=False)
+
+
+def test_product_sources_do_not_import_oracle():
+    pkg = ROOT / "video-based-gait-analysis-for-dementia_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        txt = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+
+
+def test_tables_match_oracle_and_golden(golden):
+    g = golden("kp_utils")
+    assert kp_utils.get_spin2_joint_names() == g["spin2_names"].tolist() == OK.SPIN2_NAMES
+    assert kp_utils.get_kinectv2_joint_names() == g["kinectv2_names"].tolist()
+    assert kp_utils.SPIN2_TO_KINECTV2 == g["gather"].tolist()
+    assert kp_utils.get_kinectv2_skeleton().tolist() == g["kinectv2_skeleton"].tolist()
+    t = golden("smpl_tables")
+    assert PS.JOINT_NAMES == t["joint_names"].tolist()
+    assert PS.JOINT_MAP == dict(zip(t["joint_map_keys"].tolist(), t["joint_map_vals"].tolist()))
+    assert PS.H36M_TO_J14 == t["h36m_to_j14"].tolist() and PS.H36M_TO_J17 == t["h36m_to_j17"].tolist()
+    with pytest.raises(NameError):
+        kp_utils.gather_indices("spin2", "nope")
+
+
+def test_state_dict_keys_match_reference_layout(smpl_data):
+    from gaitb200.regressor import Regressor, VPRegressor
+    from gaitb200.temporal import TemporalEncoder
+    mean = synthetic.make_mean_params()
+    mine = Regressor(mean, smpl_data)
+    keys = set(mine.state_dict().keys())
+    for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "decpose.weight", "decpose.bias",
+              "decshape.weight", "decshape.bias", "deccam.weight", "deccam.bias", "init_pose", "init_shape",
+              "init_cam", "smpl.v_template", "smpl.shapedirs", "smpl.posedirs", "smpl.J_regressor",
+              "smpl.lbs_weights", "smpl.parents", "smpl.faces_tensor", "smpl.J_regressor_extra",
+              "smpl.betas", "smpl.global_orient", "smpl.body_pose", "smpl.vertex_joint_selector.extra_joints_idxs"):
+        assert k in keys, k
+    assert mine.init_pose.shape == (1, 144) and mine.init_shape.shape == (1, 10) and mine.init_cam.shape == (1, 3)
+    # loads the synthetic checkpoint strictly for the MLP part
+    state = synthetic.make_regressor_state(seed=0)
+    res = mine.load_state_dict(state, strict=False)
+    assert not res.unexpected_keys
+    # oracle regressor (restating spin.py) exposes the same MLP / init keys
+    ork = set(OR.Regressor(smpl_data, mean).state_dict().keys())
+    assert {k for k in ork if not k.startswith("smpl.")} <= keys
+    vp = VPRegressor(smpl_model_dir=smpl_data)
+    assert "smpl.smpl.J_regressor_extra" in vp.state_dict() and "smpl.smpl.lbs_weights" in vp.state_dict()
+    enc = TemporalEncoder(n_layers=2, hidden_size=32, bidirectional=True, input_size=48)
+    assert {"gru.weight_ih_l0", "gru.weight_hh_l1_reverse", "linear.weight"} <= set(enc.state_dict().keys())
+    assert tuple(mine.smpl.joint_map.tolist()) == tuple(OS.SMPL(smpl_data).joint_map.tolist())
+    assert PS.SMPL.extra is True and PS.SMPL.kinectv2 is True

@@ -1,0 +1,370 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle and the reference-generated
+golden vectors.  Tolerances are BASELINE.json's: max-abs <= 1e-4 on vertices / joints,
+<= 1e-5 on rotation matrices (FP32 vs FP32; the only differences are summation order and FMA
+contraction).  Needs a B200: run with `pytest -m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from gaitb200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL_V = 1e-4       # vertices, joints (metres)
+TOL_R = 1e-5       # rotation matrices
+TOL_AA = 5e-5      # axis-angle (radians; conditioning of atan2 near pi)
+TOL_2D = 1e-4      # kp_2d in [-1,1] crop units
+
+T = torch.from_numpy
+
+
+def dev(a):
+    a = T(a) if isinstance(a, np.ndarray) else a
+    return a.cuda()
+
+
+def maxerr(a, b):
+    a = a.detach().cpu() if torch.is_tensor(a) else T(np.asarray(a))
+    b = b.detach().cpu() if torch.is_tensor(b) else T(np.asarray(b))
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.numel() == 0:
+        return 0.0
+    d = (a.double() - b.double()).abs()
+    d[torch.isnan(a) & torch.isnan(b)] = 0
+    return float(d.max())
+
+
+@pytest.fixture(scope="module")
+def lib_loaded():
+    from gaitb200 import _lib
+    _lib.require_device()
+    return _lib
+
+
+# ------------------------------------------------------------------------------- geometry
+def test_geometry_vs_reference_golden(golden, lib_loaded):
+    from gaitb200 import geometry as G
+    g = golden("geometry")
+    n0 = lib_loaded.launch_count()
+    assert maxerr(G.rot6d_to_rotmat(dev(g["rot6d"])), g["rot6d_to_rotmat"]) <= TOL_R
+    assert maxerr(G.rot6d_to_rotmat_spin(dev(g["rot6d"][:60])), g["rot6d_to_rotmat_spin"]) <= TOL_R
+    assert maxerr(G.rotmat_to_rot6d(dev(g["rot6d_to_rotmat"])), g["rotmat_to_rot6d"]) == 0.0
+    assert maxerr(G.batch_rodrigues(dev(g["aa"])), g["batch_rodrigues"]) <= TOL_R
+    assert maxerr(G.rotation_matrix_to_quaternion(dev(g["Rall"])), g["rotation_matrix_to_quaternion"]) <= TOL_R
+    assert maxerr(G.rotation_matrix_to_angle_axis(dev(g["Rall"])), g["rotation_matrix_to_angle_axis"]) <= TOL_AA
+    assert maxerr(G.quaternion_to_angle_axis(dev(g["qin"])), g["quaternion_to_angle_axis"]) <= TOL_AA
+    assert maxerr(G.quat2mat(dev(g["qin"])), g["quat2mat"]) <= TOL_R
+    assert maxerr(G.projection(dev(g["pts"]), dev(g["cam"])), g["projection"]) <= TOL_2D
+    assert maxerr(G.convert_weak_perspective_to_perspective(dev(g["cam"])),
+                  g["convert_weak_perspective_to_perspective"]) <= 1e-5
+    assert maxerr(G.convert_weak_perspective_to_perspective(dev(g["cam"]), 1000., 256), g["cwp_1000_256"]) <= 1e-5
+    pp = G.perspective_projection(dev(g["pts"]), dev(g["pp_rot"]), dev(g["pp_trans"]), 1234.5, dev(g["pp_center"]))
+    assert maxerr(pp, g["perspective_projection"]) <= 1e-3          # pixels, |values| ~ 1e2
+    assert lib_loaded.launch_count() - n0 >= 13                      # the CUDA library did the work
+
+
+def test_geometry_vs_oracle_bulk_and_edges(lib_loaded):
+    from gaitb200 import geometry as G
+    from oracle import geometry as OG
+    from oracle import smplx_lbs as OL
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 31, 24 * 1024):
+        x = torch.tensor([1., 0, 0, 1, 0, 0]) + 0.5 * torch.randn(n, 6, generator=g)
+        R = OG.rot6d_to_rotmat(x)
+        assert maxerr(G.rot6d_to_rotmat(x.cuda()), R) <= TOL_R
+        assert maxerr(G.rotation_matrix_to_angle_axis(R.cuda()), OG.rotation_matrix_to_angle_axis(R)) <= TOL_AA
+        aa = torch.randn(n, 3, generator=g)
+        assert maxerr(G.batch_rodrigues_smplx(aa.cuda()), OL.batch_rodrigues(aa)) <= TOL_R
+        assert maxerr(G.batch_rodrigues(aa.cuda()), OG.batch_rodrigues(aa)) <= TOL_R
+    # (N,3,4) input, empty input, zero / degenerate 6-vectors (eps clamp)
+    R34 = torch.cat([OG.rot6d_to_rotmat(torch.randn(9, 6, generator=g)), torch.zeros(9, 3, 1)], dim=2)
+    assert maxerr(G.rotation_matrix_to_angle_axis(R34.cuda()), OG.rotation_matrix_to_angle_axis(R34)) <= TOL_AA
+    assert G.rot6d_to_rotmat(torch.zeros(0, 6).cuda()).shape == (0, 3, 3)
+    z = torch.tensor([[0., 0, 0, 0, 0, 0], [1., 2, 0, 0, 0, 0], [1e-7, 0, 0, 1e-7, 0, 0]])
+    assert maxerr(G.rot6d_to_rotmat(z.cuda()), OG.rot6d_to_rotmat(z)) <= TOL_R
+    # zero rotation vector: NaN/0 handling identical to the reference route
+    a0 = torch.zeros(2, 3)
+    assert maxerr(G.batch_rodrigues_smplx(a0.cuda()), OL.batch_rodrigues(a0)) <= TOL_R
+
+
+def test_convert_kps_on_device(golden, lib_loaded):
+    from gaitb200.kp_utils import convert_kps
+    g = golden("kp_utils")
+    out = convert_kps(dev(g["joints"]), "spin2", "kinectv2")
+    assert out.shape == (7, 25, 3)
+    assert maxerr(out, g["spin2_to_kinectv2"].astype(np.float32)) == 0.0
+
+
+# ------------------------------------------------------------------------------- linear / GRU
+@pytest.mark.parametrize("M,N,K", [(1, 7, 5), (3, 157, 1024), (64, 6144, 2048), (130, 130, 2205), (1024, 1024, 160),
+                                   (257, 20670, 224)])
+def test_linear_vs_torch_fp32(M, N, K, lib_loaded):
+    L = lib_loaded
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    Cin = torch.randn(M, N, generator=g)
+    ref = A.double() @ W.double().T + b.double() + Cin.double()
+    Ad, Wd, bd, Cd = A.cuda(), W.cuda(), b.cuda(), Cin.cuda()
+    out = torch.empty(M, N, device="cuda")
+    L.call("gait_linear", Ad.data_ptr(), K, Wd.data_ptr(), K, bd.data_ptr(), Cd.data_ptr(), N, out.data_ptr(), N,
+           M, N, K, L.stream_ptr())
+    # fp32 accumulation error of a K-long dot product of O(1) terms
+    assert maxerr(out, ref.float()) <= 2e-5 * max(1.0, K ** 0.5 / 8)
+    # in-place residual (Cin aliases C) as the regressor uses it
+    L.call("gait_linear", Ad.data_ptr(), K, Wd.data_ptr(), K, None, Cd.data_ptr(), N, Cd.data_ptr(), N, M, N, K,
+           L.stream_ptr())
+    assert maxerr(Cd, (A.double() @ W.double().T + Cin.double()).float()) <= 2e-5 * max(1.0, K ** 0.5 / 8)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(S=2, T=5, I=32, H=32, layers=1, bi=False),
+    dict(S=3, T=7, I=48, H=20, layers=2, bi=True),            # ragged sizes, not multiples of 4 per gate
+    dict(S=4, T=6, I=3072, H=300, layers=2, bi=True),         # BidirectionalModel.rnn (gait_feat_encoder.py:51-57)
+    dict(S=1, T=16, I=2048, H=2048, layers=1, bi=False),      # C1
+])
+def test_gru_vs_torch(cfg, lib_loaded):
+    from gaitb200.temporal import gru_forward
+    torch.manual_seed(3)
+    gru = torch.nn.GRU(cfg["I"], cfg["H"], num_layers=cfg["layers"], bidirectional=cfg["bi"]).eval()
+    x = torch.randn(cfg["S"], cfg["T"], cfg["I"]) * 0.5
+    with torch.no_grad():
+        ref, _ = gru(x.permute(1, 0, 2))
+    y, _ = gru_forward(gru.cuda(), x.cuda())
+    assert maxerr(y, ref.permute(1, 0, 2)) <= 2e-5
+
+
+def test_temporal_encoder_variants(lib_loaded):
+    from gaitb200.temporal import TemporalEncoder
+    from oracle.temporal import TemporalEncoder as OT
+    for kw in (dict(hidden_size=64, input_size=64), dict(hidden_size=40, input_size=64, add_linear=True),
+               dict(hidden_size=24, input_size=64, bidirectional=True, n_layers=2),
+               dict(hidden_size=64, input_size=64, use_residual=False)):
+        torch.manual_seed(11)
+        o = OT(**kw).eval()
+        m = TemporalEncoder(**kw).eval()
+        m.load_state_dict(o.state_dict())
+        x = torch.randn(3, 9, 64)
+        with torch.no_grad():
+            ref = o(x)
+        assert maxerr(m.cuda()(x.cuda()), ref) <= 2e-5, kw
+
+
+# ------------------------------------------------------------------------------- SMPL
+@pytest.mark.parametrize("variant,F", [("sparse", 1), ("sparse", 7), ("dense", 9), ("sparse", 64)])
+def test_smpl_vs_oracle(variant, F, lib_loaded):
+    from gaitb200.smpl import SMPL
+    from oracle import geometry as OG
+    from oracle import smpl as OS
+    data = synthetic.make_smpl_data(seed=2, variant=variant)
+    rot6d, betas, cam = synthetic.make_pose_inputs(F, seed=F, noise=0.4)
+    R = OG.rot6d_to_rotmat(rot6d).view(F, 24, 3, 3)
+    o, m = OS.SMPL(data), SMPL(data).cuda()
+    for kin, extra, J in ((True, True, 29), (False, True, 49), (True, False, 45)):
+        o.kinectv2 = m.kinectv2 = kin
+        o.extra = m.extra = extra
+        with torch.no_grad():
+            ref = o(betas=betas, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+        out = m(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
+        assert out.joints.shape == (F, J, 3) and out.vertices.shape == (F, 6890, 3)
+        assert maxerr(out.vertices, ref.vertices) <= TOL_V
+        assert maxerr(out.joints, ref.joints) <= TOL_V
+    # pose2rot=True (Rodrigues path used by lib/utils/smooth_pose.py:72-76)
+    o.kinectv2 = m.kinectv2 = True
+    o.extra = m.extra = True
+    aa = 0.4 * torch.randn(F, 72, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = o(betas=betas, body_pose=aa[:, 3:], global_orient=aa[:, :3], pose2rot=True)
+    out = m(betas=betas.cuda(), body_pose=aa[:, 3:].cuda(), global_orient=aa[:, :3].cuda(), pose2rot=True)
+    assert maxerr(out.vertices, ref.vertices) <= TOL_V and maxerr(out.joints, ref.joints) <= TOL_V
+
+
+def test_smpl_wrapper_vs_reference_golden(golden, smpl_data, lib_loaded):
+    from gaitb200.smpl import SMPL, SMPLHead
+    g = golden("smpl_wrapper")
+    smpl = SMPL(smpl_data).cuda()
+    rot, betas = dev(g["rotmat"]), dev(g["betas"])
+    for kin, tag in ((True, "kin"), (False, "spin")):
+        smpl.kinectv2 = kin
+        so = smpl(betas=betas[:2], body_pose=rot[:2, 1:], global_orient=rot[:2, 0:1], pose2rot=False)
+        assert maxerr(so.vertices, g[f"smpl_{tag}_vertices"]) <= TOL_V
+        assert maxerr(so.joints, g[f"smpl_{tag}_joints"]) <= TOL_V
+    smpl.kinectv2 = True
+    aa = dev(g["smpl_aa"])
+    so = smpl(betas=betas[:2], body_pose=aa[:, 3:], global_orient=aa[:, :3], pose2rot=True)
+    assert maxerr(so.vertices, g["smpl_aa_vertices"]) <= TOL_V and maxerr(so.joints, g["smpl_aa_joints"]) <= TOL_V
+    head = SMPLHead(smpl_model_dir=smpl_data).cuda()
+    ho = head(rot[:2], betas[:2], cam=dev(g["cam"][:2]), normalize_joints2d=True)
+    assert maxerr(ho["smpl_joints2d"], g["head_joints2d_norm"]) <= TOL_2D
+    ho = head(rot[:2], betas[:2], cam=dev(g["cam"][:2]), normalize_joints2d=False)
+    assert maxerr(ho["smpl_joints2d"], g["head_joints2d"]) <= 1e-2    # pixels
+    assert maxerr(ho["smpl_joints3d"], g["head_joints3d"]) <= TOL_V
+
+
+def test_smpl_known_answers(smpl_data, lib_loaded):
+    """SURVEY section 4 KATs on the CUDA path: rest pose returns the template; a root-only
+    rotation is rigid about the root joint."""
+    from gaitb200.smpl import SMPL
+    from oracle import geometry as OG
+    smpl = SMPL(smpl_data).cuda()
+    smpl.extra = False
+    I = torch.eye(3).expand(2, 24, 3, 3).contiguous().cuda()
+    so = smpl(betas=torch.zeros(2, 10).cuda(), body_pose=I[:, 1:], global_orient=I[:, :1], pose2rot=False)
+    vt = T(smpl_data["v_template"])
+    assert maxerr(so.vertices, vt.expand(2, -1, -1)) <= 1e-6
+    J = T(smpl_data["J_regressor"]) @ vt
+    assert maxerr(so.joints[:, :24], J.expand(2, -1, -1)) <= 1e-6
+    assert maxerr(so.joints[:, 24:], vt[T(smpl_data["landmark_verts"])].expand(2, -1, -1)) <= 1e-6
+    R0 = OG.rot6d_to_rotmat(torch.randn(1, 6))[0]
+    R = torch.eye(3).repeat(1, 24, 1, 1)
+    R[0, 0] = R0
+    betas = torch.randn(1, 10)
+    so = smpl(betas=betas.cuda(), body_pose=R[:, 1:].cuda(), global_orient=R[:, :1].cuda(), pose2rot=False)
+    v_shaped = vt + torch.einsum('l,mkl->mk', betas[0], T(smpl_data["shapedirs"]))
+    J0 = (T(smpl_data["J_regressor"]) @ v_shaped)[0]
+    assert maxerr(so.vertices[0], (v_shaped - J0) @ R0.T + J0) <= 5e-6
+
+
+# ------------------------------------------------------------------------------- regressors
+def test_regressor_vs_reference_golden(golden, smpl_data, lib_loaded):
+    from gaitb200.regressor import Regressor
+    g = golden("regressor")
+    reg = Regressor(synthetic.make_mean_params(), smpl_data)
+    reg.load_state_dict(synthetic.make_regressor_state(seed=0, decoder_gain=0.3), strict=False)
+    reg = reg.cuda().eval()
+    x = dev(g["x"])
+    o = reg(x)[-1]
+    assert o["theta"].shape == (3, 85) and o["kp_3d"].shape == (3, 29, 3) and o["verts"].shape == (3, 6890, 3)
+    assert maxerr(o["rotmat"], g["reg_rotmat"]) <= TOL_R
+    assert maxerr(o["verts"], g["reg_verts"]) <= TOL_V and maxerr(o["kp_3d"], g["reg_kp_3d"]) <= TOL_V
+    assert maxerr(o["kp_2d"], g["reg_kp_2d"]) <= TOL_2D and maxerr(o["theta"], g["reg_theta"]) <= TOL_AA
+    assert maxerr(reg(x, n_iter=1)[-1]["theta"], g["reg_iter1_theta"]) <= TOL_AA
+    o = reg(x, J_regressor=dev(smpl_data["J_regressor_h36m"]))[-1]
+    assert o["kp_3d"].shape == (3, 14, 3)
+    assert maxerr(o["kp_3d"], g["reg_h36m_kp_3d"]) <= TOL_V and maxerr(o["kp_2d"], g["reg_h36m_kp_2d"]) <= TOL_2D
+
+
+def test_regressor_known_answers_and_inits(smpl_data, lib_loaded):
+    from gaitb200.regressor import Regressor
+    from oracle import regressor as OR
+    mean = synthetic.make_mean_params()
+    state = synthetic.make_regressor_state(seed=4, decoder_gain=0.2)
+    o = OR.Regressor(smpl_data, mean).eval()
+    o.load_state_dict(state, strict=False)
+    m = Regressor(mean, smpl_data)
+    m.load_state_dict(state, strict=False)
+    m = m.cuda().eval()
+    x = synthetic.make_features(1, 37, seed=8)[0]
+    # explicit per-frame initial state
+    ip = T(mean["pose"]).expand(37, -1) + 0.05 * torch.randn(37, 144)
+    ic = torch.tensor([[0.8, 0.1, -0.1]]).expand(37, -1).contiguous()
+    with torch.no_grad():
+        rp, rs, rc = o.iterate(x, init_pose=ip, init_cam=ic, n_iter=2)
+    st = m.iterate(x.cuda(), init_pose=ip.cuda(), init_cam=ic.cuda(), n_iter=2)
+    assert maxerr(st[:, :144], rp) <= TOL_R and maxerr(st[:, 144:154], rs) <= TOL_R and maxerr(st[:, 154:157], rc) <= TOL_R
+    # zero decoders: any number of iterations returns the initial state
+    for lin in (m.decpose, m.decshape, m.deccam):
+        torch.nn.init.zeros_(lin.weight); torch.nn.init.zeros_(lin.bias)
+    st = m.iterate(x.cuda(), n_iter=5)
+    assert maxerr(st[:, :144], T(mean["pose"]).expand(37, -1)) == 0.0
+    assert maxerr(st[:, 154:157], T(mean["cam"]).expand(37, -1)) == 0.0
+    m.train()
+    with pytest.raises(lib_loaded.GaitLibraryError):
+        m.iterate(x.cuda())
+
+
+def test_vpregressor_vs_reference_golden(golden, smpl_data, lib_loaded):
+    from gaitb200.regressor import SMPLRegressor, VPRegressor
+    g = golden("vpregressor")
+    patt = {"pred_pose": dev(g["rotmat"]), "pred_shape": dev(g["betas"]), "pred_cam": dev(g["cam"])}
+    vp = VPRegressor(smpl_model_dir=smpl_data).cuda()
+    o = vp(dict(patt), batch_size=2)
+    assert isinstance(o, list) and len(o) == 1
+    o = o[-1]
+    assert o["theta"].shape == (2, 2, 85) and o["verts"].shape == (2, 2, 6890, 3)
+    assert o["kp_3d"].shape == (2, 2, 29, 3) and o["kp_2d"].shape == (2, 2, 29, 2) and o["rotmat"].shape == (2, 2, 24, 3, 3)
+    assert maxerr(o["verts"], g["vp_verts"]) <= TOL_V and maxerr(o["kp_3d"], g["vp_kp_3d"]) <= TOL_V
+    assert maxerr(o["theta"], g["vp_theta"]) <= TOL_AA and maxerr(o["kp_2d"], g["vp_kp_2d"]) <= TOL_2D
+    assert maxerr(o["rotmat"], g["vp_rotmat"]) == 0.0
+    o = vp(dict(patt, pred_avg=torch.ones(1), pred_phase=torch.zeros(1)), batch_size=2,
+           J_regressor=dev(smpl_data["J_regressor_h36m"]))[-1]
+    assert o["kp_3d"].shape == (2, 2, 14, 3) and "pred_avg" in o and "pred_phase" in o
+    assert maxerr(o["kp_3d"], g["vp_h36m_kp_3d"]) <= TOL_V
+    sr = SMPLRegressor(smpl_model_dir=smpl_data).cuda()
+    o = sr({"pred_rotmat": patt["pred_pose"], "pred_shape": patt["pred_shape"], "pred_cam": patt["pred_cam"]}, batch_size=1)
+    assert maxerr(o["verts"], g["sr_verts"]) <= TOL_V and maxerr(o["kp_3d"], g["sr_kp_3d"]) <= TOL_V
+
+
+# ------------------------------------------------------------------------------- whole path
+def _heads(variant="sparse", gain=0.3):
+    from gaitb200.head import GaitHead
+    from oracle.head import GaitHeadOracle
+    data = synthetic.make_smpl_data(seed=0, variant=variant)
+    mean = synthetic.make_mean_params()
+    rs = synthetic.make_regressor_state(seed=0, decoder_gain=gain)
+    gs = synthetic.make_gru_state(seed=0)
+    return GaitHead(data, mean, rs, gs).cuda(), GaitHeadOracle(data, mean, rs, gs), data
+
+
+def _check_head(out, ref):
+    assert maxerr(out["rotmat"], ref["rotmat"]) <= TOL_R
+    assert maxerr(out["verts"], ref["verts"]) <= TOL_V
+    assert maxerr(out["kp_3d"], ref["kp_3d"]) <= TOL_V
+    assert maxerr(out["kinect25"], ref["kinect25"]) <= TOL_V
+    assert maxerr(out["kp_2d"], ref["kp_2d"]) <= TOL_2D
+    assert maxerr(out["theta"], ref["theta"]) <= TOL_AA
+
+
+@pytest.mark.parametrize("S,T_", [(1, 16), (3, 5), (8, 16)])
+def test_head_vs_oracle(S, T_, lib_loaded):
+    """C1 (1x16, the reference's CPU-runnable config) and ragged small batches, eager launches."""
+    head, oracle, _ = _heads()
+    feats = synthetic.make_features(S, T_, seed=1234)
+    out = head(feats.cuda())
+    assert out["verts"].shape == (S, T_, 6890, 3) and out["kinect25"].shape == (S, T_, 25, 3)
+    _check_head(out, oracle(feats))
+
+
+def test_head_graph_replay_dense_variant(lib_loaded):
+    """CUDA-graph replay gives the same answer as the oracle on the dense-weights SMPL variant,
+    and a second replay with new input is not stale."""
+    head, oracle, _ = _heads(variant="dense")
+    head.capture(4, 16)
+    assert head.launches_per_step > 0
+    for seed in (1, 2):
+        feats = synthetic.make_features(4, 16, seed=seed)
+        head.input.copy_(feats.cuda())
+        head.step()
+        torch.cuda.synchronize()
+        _check_head(head.outputs(), oracle(feats))
+
+
+def test_full_size_properties_c2(lib_loaded):
+    """BASELINE config 2 (64 x 16 frames, full mesh): size-independent properties.
+    (a) every rotation matrix is orthonormal with det +1; (b) Kinect-25 is the spin2 gather of
+    kp_3d; (c) kp_3d[:, 24:28] are the landmark vertices of verts; (d) kp_2d re-derives from
+    kp_3d and theta's camera; (e) theta's betas/cam slices equal the regressor state;
+    (f) a 16-frame slice agrees with the oracle."""
+    from gaitb200.kp_utils import SPIN2_TO_KINECTV2
+    head, oracle, data = _heads()
+    feats = synthetic.make_features(64, 16, seed=1234)
+    out = {k: v.clone() for k, v in head(feats.cuda()).items()}
+    R = out["rotmat"].reshape(-1, 3, 3)
+    eye = torch.eye(3, device="cuda").expand_as(R)
+    assert float((R.transpose(1, 2) @ R - eye).abs().max()) <= 1e-5
+    assert float((torch.linalg.det(R) - 1).abs().max()) <= 1e-5
+    assert torch.equal(out["kinect25"], out["kp_3d"][:, :, SPIN2_TO_KINECTV2])
+    lm = data["landmark_verts"]
+    picks = [int(lm[35 - 24]), int(lm[37 - 24]), int(lm[40 - 24]), int(lm[42 - 24])]
+    assert torch.equal(out["kp_3d"][:, :, 24:28], out["verts"][:, :, picks])
+    thorax = torch.einsum('v,stvc->stc', dev(data["J_regressor_extra"][5]), out["verts"])
+    assert maxerr(out["kp_3d"][:, :, 28], thorax) <= 1e-5
+    cam = out["theta"][..., :3]
+    tz = 2 * 5000. / (224. * cam[..., 0] + 1e-9)
+    P = out["kp_3d"] + torch.stack([cam[..., 1], cam[..., 2], tz], -1)[:, :, None]
+    assert maxerr(out["kp_2d"], 5000. * P[..., :2] / P[..., 2:] / 112.) <= 1e-4
+    assert torch.isfinite(out["verts"]).all()
+    ref = oracle(feats[:1])
+    sl = {k: v[:1] for k, v in out.items()}
+    _check_head(sl, ref)

@@ -1,0 +1,125 @@
+"""ctypes binding of the C-ABI CUDA library (include/gaitb200.h).
+
+The library is built in-tree (``make`` / ``__graft_entry__.build()``) as
+``lib/libgaitb200.so``.  There is no other implementation behind this module: if the
+library is missing, or a tensor is not an FP32 CUDA tensor, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("GAITB200_LIB", _HERE / "lib" / "libgaitb200.so"))
+
+P, I32, I64, F32, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+# name -> argtypes (every function returns int unless listed in _RESTYPES)
+_SIGS = {
+    "gait_abi_version": [],
+    "gait_error_string": [I32],
+    "gait_last_error": [],
+    "gait_device_info": [C.POINTER(I32), C.POINTER(I32), C.POINTER(I32)],
+    "gait_launch_count": [],
+    "gait_rot6d_to_rotmat": [P, I32, I64, P, I64, F32, P],
+    "gait_rotmat_to_rot6d": [P, P, I64, P],
+    "gait_rotmat_to_quaternion": [P, I32, P, I64, F32, P],
+    "gait_quaternion_to_axis_angle": [P, P, I64, P],
+    "gait_rotmat_to_axis_angle": [P, I32, P, I64, I32, I64, I32, P],
+    "gait_quat2mat": [P, P, I64, P],
+    "gait_batch_rodrigues": [P, P, I64, I32, P],
+    "gait_weak_perspective_to_translation": [P, P, I64, F32, F32, P],
+    "gait_perspective_projection": [P, P, P, P, F32, F32, P, I64, I32, P],
+    "gait_linear": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I64, P],
+    "gait_gru_workspace_bytes": [I64, I64, I64],
+    "gait_gru_layer": [P, I64, P, P, P, P, P, P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I32, P, SZ, P],
+    "gait_relu": [P, P, I64, P],
+    "gait_hmr_workspace_bytes": [I64, I64],
+    "gait_hmr_regressor": [P, I64, P, P, P, P, P, P, P, P, I64, I32, P, I64, I64, I64, P, SZ, P],
+    "gait_smpl_pose_chain": [P, P, I64, P, P, P, P, P, P, I64, P],
+    "gait_smpl_blend": [P, P, P, I64, I64, P],
+    "gait_smpl_lbs": [P, P, P, P, I64, I64, P],
+    "gait_joint_regress": [P, P, P, I64, I64, I32, P],
+    "gait_joints_assemble": [P, P, I64, P, I32, P, I32, P, I32, P, P, I64, F32, F32, F32, P, P, I32, P, I64, P],
+    "gait_gather_joints": [P, I32, P, I32, P, I64, P],
+    "gait_pack_theta": [P, P, I64, P, I64, P, I64, P],
+}
+_RESTYPES = {
+    "gait_error_string": C.c_char_p,
+    "gait_last_error": C.c_char_p,
+    "gait_launch_count": I64,
+    "gait_gru_workspace_bytes": SZ,
+    "gait_hmr_workspace_bytes": SZ,
+}
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+class GaitLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load lib/libgaitb200.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise GaitLibraryError(
+            f"{LIB_PATH} is missing: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "gaitb200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, argtypes in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, I32)
+    if lib.gait_abi_version() != 1:
+        raise GaitLibraryError(f"ABI version mismatch: library reports {lib.gait_abi_version()}")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point; raise on a negative return code."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        detail = lib.gait_last_error().decode(errors="replace")
+        kind = lib.gait_error_string(rc).decode()
+        raise GaitLibraryError(f"{name} failed ({rc}: {kind}): {detail}")
+
+
+def launch_count() -> int:
+    return int(load().gait_launch_count())
+
+
+def require_device():
+    """Fail loudly unless a CUDA sm_100 device is current."""
+    if not torch.cuda.is_available():
+        raise GaitLibraryError("gaitb200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    sm, major, minor = I32(), I32(), I32()
+    call("gait_device_info", C.byref(sm), C.byref(major), C.byref(minor))
+    return sm.value, major.value, minor.value
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32(t, name: str = "tensor") -> torch.Tensor:
+    """Validate an input: FP32 CUDA tensor, made contiguous."""
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise GaitLibraryError(f"{name}: expected a CUDA tensor (gaitb200 has no CPU path), got device {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,61 @@
+// Shared helpers for the gaitb200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "gaitb200.h"
+
+namespace gait {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline cudaStream_t as_stream(gait_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Check the launch that was just enqueued; records the error text for gait_last_error().
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return GAIT_ERR_CUDA;
+    }
+    count_launch();
+    return GAIT_OK;
+}
+
+#define GAIT_REQUIRE(cond, ...)                  \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::gait::set_error(__VA_ARGS__);      \
+            return GAIT_ERR_INVALID;             \
+        }                                        \
+    } while (0)
+
+#define GAIT_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            ::gait::set_error("%s: %s", #call, cudaGetErrorString(e__));             \
+            return GAIT_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+#define GAIT_TRY(call)                 \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != GAIT_OK) return rc__; \
+    } while (0)
+
+// internal (not exported) variants used by composite entry points
+int linear_launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                  const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                  cudaStream_t stream);
+
+}  // namespace gait

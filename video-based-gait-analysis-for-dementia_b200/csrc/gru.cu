@@ -1,0 +1,108 @@
+// gait_gru_layer: one layer / one direction of torch.nn.GRU (gate order r,z,n;
+// h' = (1-z) n + z h), the arithmetic behind TemporalEncoder and
+// lib/models/layers/gait_feat_encoder.py:51-57,88.
+//
+// Input projection for all S*T frames is one GEMM; the recurrence is T steps of
+// (S,H).(H,3H) plus a fused gate kernel that also emits the TemporalEncoder residual sum.
+#include "common.cuh"
+
+namespace gait {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// gi: (S*T, 3H) input projection incl. b_ih; gh: (S, 3H) hidden projection incl. b_hh, or NULL at
+// the first step with h0 == NULL (then gh == b_hh).
+__global__ void gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                const float* __restrict__ b_hh, const float* __restrict__ hprev, int64_t ldh,
+                                float* __restrict__ y, int64_t ldy, const float* __restrict__ resid, int64_t ldres,
+                                float* __restrict__ out, int64_t ldout, float* __restrict__ hn, int S, int T,
+                                int H, int t) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (u >= H) return;
+    const int64_t f = (int64_t)s * T + t;
+    const float* g = gi + f * 3 * H;
+    float hr, hz, hnn;
+    if (gh) {
+        const float* q = gh + (int64_t)s * 3 * H;
+        hr = q[u]; hz = q[H + u]; hnn = q[2 * H + u];
+    } else {
+        hr = b_hh[u]; hz = b_hh[H + u]; hnn = b_hh[2 * H + u];
+    }
+    const float hp = hprev ? hprev[(int64_t)s * ldh + u] : 0.f;
+    const float r = sigmoidf_(g[u] + hr);
+    const float z = sigmoidf_(g[H + u] + hz);
+    const float n = tanhf(g[2 * H + u] + r * hnn);
+    const float h = (1.f - z) * n + z * hp;
+    y[f * ldy + u] = h;
+    if (out) out[f * ldout + u] = h + resid[f * ldres + u];
+    if (hn) hn[(int64_t)s * H + u] = h;
+}
+
+__global__ void relu_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fmaxf(x[i], 0.f);
+}
+
+}  // namespace gait
+
+using namespace gait;
+
+extern "C" {
+
+int gait_relu(const float* x, float* y, int64_t n, gait_stream_t stream) {
+    GAIT_REQUIRE(n >= 0 && (n == 0 || (x && y)), "relu: null pointer or negative n");
+    if (n == 0) return GAIT_OK;
+    relu_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(x, y, n);
+    return check_launch("relu");
+}
+
+size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H) {
+    if (S <= 0 || T <= 0 || H <= 0) return 0;
+    return (size_t)(S * T * 3 * H + S * 3 * H) * sizeof(float);
+}
+
+int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* W_hh, const float* b_ih,
+                   const float* b_hh, const float* h0, float* y, int64_t ldy, const float* resid,
+                   int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T, int64_t I,
+                   int64_t H, int reverse, void* workspace, size_t workspace_bytes, gait_stream_t stream) {
+    GAIT_REQUIRE(S >= 0 && T >= 0 && I > 0 && H > 0, "gru_layer: bad sizes");
+    if (S == 0 || T == 0) return GAIT_OK;
+    GAIT_REQUIRE(x && W_ih && W_hh && b_ih && b_hh && y && workspace, "gru_layer: null pointer");
+    GAIT_REQUIRE(ldx >= I && ldy >= H, "gru_layer: stride smaller than row");
+    GAIT_REQUIRE(out == nullptr || (resid != nullptr && ldout >= H && ldres >= H), "gru_layer: out needs resid and strides");
+    GAIT_REQUIRE(S < 65536, "gru_layer: at most 65535 sequences per call");
+    if (workspace_bytes < gait_gru_workspace_bytes(S, T, H)) {
+        set_error("gru_layer: workspace %zu < %zu bytes", workspace_bytes, gait_gru_workspace_bytes(S, T, H));
+        return GAIT_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    float* gi = static_cast<float*>(workspace);
+    float* gh = gi + S * T * 3 * H;
+    const int64_t F = S * T;
+    // gi = x . W_ih^T + b_ih for every frame
+    GAIT_TRY(linear_launch(x, ldx, W_ih, I, b_ih, nullptr, 0, gi, 3 * H, F, 3 * H, I, st));
+    const dim3 block(256), grid((unsigned)ceil_div(H, 256), (unsigned)S);
+    for (int64_t step = 0; step < T; ++step) {
+        const int64_t t = reverse ? (T - 1 - step) : step;
+        const float* hprev = nullptr;
+        int64_t ldh = 0;
+        if (step == 0) {
+            hprev = h0; ldh = H;
+        } else {
+            const int64_t tp = reverse ? t + 1 : t - 1;
+            hprev = y + tp * ldy; ldh = T * ldy;        // row s of h_{t-1} is y[s, tp, :]
+        }
+        const float* ghp = nullptr;
+        if (hprev) {
+            GAIT_TRY(linear_launch(hprev, ldh, W_hh, H, b_hh, nullptr, 0, gh, 3 * H, S, 3 * H, H, st));
+            ghp = gh;
+        }
+        gru_gate_kernel<<<grid, block, 0, st>>>(gi, ghp, b_hh, hprev, ldh, y, ldy, resid, ldres, out, ldout,
+                                                (step == T - 1) ? hn : nullptr, (int)S, (int)T, (int)H, (int)t);
+        GAIT_TRY(check_launch("gru_gate"));
+    }
+    return GAIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// gait_hmr_regressor: the iterative HMR/VIBE regressor loop of lib/models/spin.py:244-265.
+//
+//   for it in range(n_iter):
+//       xc = cat([x, pose, shape, cam]); h = fc2(fc1(xc)); state += dec(h)
+//
+// fc1 is split column-wise: the x part (Din of the 2205 columns) does not change between
+// iterations, so x.W1x^T + b1 is computed once; each iteration then needs only the 157-column
+// state part.  There is no non-linearity between the layers (dropout is the identity in eval),
+// exactly as in the reference.  The three decoders are one (157,Dh) matrix.
+#include "common.cuh"
+
+namespace gait {
+
+constexpr int kState = 157;
+constexpr int kStateLd = 160;
+
+__global__ void broadcast_state_kernel(const float* __restrict__ init, int64_t init_rows, float* __restrict__ state,
+                                       int64_t F) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= F * kStateLd) return;
+    const int64_t f = i / kStateLd;
+    const int c = (int)(i % kStateLd);
+    const float v = (c < kState) ? init[(init_rows == 1 ? 0 : f) * kStateLd + c] : 0.f;
+    state[i] = v;
+}
+
+}  // namespace gait
+
+using namespace gait;
+
+extern "C" {
+
+size_t gait_hmr_workspace_bytes(int64_t F, int64_t Dh) {
+    if (F <= 0 || Dh <= 0) return 0;
+    return (size_t)(3 * F * Dh) * sizeof(float);
+}
+
+int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const float* W1s, const float* b1,
+                       const float* W2, const float* b2, const float* Wd, const float* bd,
+                       const float* init, int64_t init_rows, int n_iter, float* state_out, int64_t F,
+                       int64_t Din, int64_t Dh, void* workspace, size_t workspace_bytes,
+                       gait_stream_t stream) {
+    GAIT_REQUIRE(F >= 0 && Din > 0 && Dh > 0 && n_iter >= 0, "hmr_regressor: bad sizes");
+    if (F == 0) return GAIT_OK;
+    GAIT_REQUIRE(x && W1x && W1s && b1 && W2 && b2 && Wd && bd && init && state_out && workspace,
+                 "hmr_regressor: null pointer");
+    GAIT_REQUIRE(init_rows == 1 || init_rows == F, "hmr_regressor: init must have 1 or F rows");
+    GAIT_REQUIRE(ldx >= Din, "hmr_regressor: ldx < Din");
+    if (workspace_bytes < gait_hmr_workspace_bytes(F, Dh)) {
+        set_error("hmr_regressor: workspace %zu < %zu bytes", workspace_bytes, gait_hmr_workspace_bytes(F, Dh));
+        return GAIT_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    float* hx = static_cast<float*>(workspace);
+    float* h1 = hx + F * Dh;
+    float* h2 = h1 + F * Dh;
+    broadcast_state_kernel<<<(unsigned)ceil_div(F * kStateLd, 256), 256, 0, st>>>(init, init_rows, state_out, F);
+    GAIT_TRY(check_launch("hmr broadcast_state"));
+    if (n_iter == 0) return GAIT_OK;
+    // iteration-invariant part of fc1
+    GAIT_TRY(linear_launch(x, ldx, W1x, Din, b1, nullptr, 0, hx, Dh, F, Dh, Din, st));
+    for (int it = 0; it < n_iter; ++it) {
+        GAIT_TRY(linear_launch(state_out, kStateLd, W1s, kStateLd, nullptr, hx, Dh, h1, Dh, F, Dh, kStateLd, st));
+        GAIT_TRY(linear_launch(h1, Dh, W2, Dh, b2, nullptr, 0, h2, Dh, F, Dh, Dh, st));
+        GAIT_TRY(linear_launch(h2, Dh, Wd, Dh, bd, state_out, kStateLd, state_out, kStateLd, F, kState, Dh, st));
+    }
+    return GAIT_OK;
+}
+
+}  // extern "C"

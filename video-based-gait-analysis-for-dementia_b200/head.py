@@ -1,0 +1,190 @@
+"""GaitHead - the whole hot path as one object: backbone features -> TemporalEncoder ->
+Regressor (MLP loop, rot6d->R, SMPL, projection, axis-angle) -> Kinect-25 joints.
+
+It owns a TemporalEncoder and a Regressor (the reference-API modules; their parameters and
+buffers are the single source of truth) and runs them for a FIXED (S, T) through the C-ABI
+with every intermediate pre-allocated, so a step is a fixed sequence of kernel launches on one
+stream - which is what gets captured into a CUDA graph and replayed.  Output keys/shapes follow
+spin.Regressor's dict (spin.py:288-295) reshaped to (S,T,...), plus 'kinect25'
+(convert_kps(kp_3d,'spin2','kinectv2'), batch_generation.py:323).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .kp_utils import SPIN2_TO_KINECTV2
+from .regressor import Regressor
+from .temporal import TemporalEncoder
+
+_STATE_LD = 160
+
+
+class GaitHead(nn.Module):
+    def __init__(self, smpl_data, mean_params, regressor_state=None, gru_state=None, write_mesh=True,
+                 n_iter=3, **encoder_kw):
+        super().__init__()
+        self.encoder = TemporalEncoder(**encoder_kw)
+        self.regressor = Regressor(mean_params, smpl_data)
+        if gru_state is not None:
+            self.encoder.gru.load_state_dict(gru_state)
+        if regressor_state is not None:
+            self.regressor.load_state_dict(regressor_state, strict=False)
+        g = self.encoder.gru
+        if g.num_layers != 1 or g.bidirectional or self.encoder.linear is not None or g.hidden_size != g.input_size:
+            raise L.GaitLibraryError("GaitHead fuses the 1-layer unidirectional residual TemporalEncoder; "
+                                     "use TemporalEncoder + Regressor separately for other encoders")
+        self.n_iter = n_iter
+        self.write_mesh = write_mesh
+        self.eval()
+        self._plan = None
+        self._graph = None
+
+    # ------------------------------------------------------------------ buffers for one (S,T)
+    def plan(self, S: int, T: int):
+        dev = self.regressor.fc1.weight.device
+        if dev.type != "cuda":
+            raise L.GaitLibraryError("GaitHead is on %s; move it to a CUDA device (no CPU path)" % dev)
+        L.require_device()
+        lib = L.load()
+        F = S * T
+        H = self.encoder.gru.hidden_size
+        V = self.regressor.smpl.v_template.shape[0]
+        e = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
+        gru_bytes = lib.gait_gru_workspace_bytes(S, T, H)
+        hmr_bytes = lib.gait_hmr_workspace_bytes(F, self.regressor.fc1.out_features)
+        p = {
+            "S": S, "T": T, "F": F, "V": V, "dev": dev,
+            "x": e(S, T, H), "y_raw": e(S, T, H), "enc": e(S, T, H),
+            "ws": e(max(gru_bytes, hmr_bytes, 4) // 4), "gru_bytes": gru_bytes, "hmr_bytes": hmr_bytes,
+            "state": e(F, _STATE_LD), "rotmat": e(F, 24, 3, 3), "A": e(F, 24, 12), "Jp": e(F, 24, 3),
+            "coef": e(F, 224), "v_posed": e(F, V, 3), "verts": e(F, V, 3), "extra": e(F, 1, 3),
+            "joints": e(F, 29, 3), "kp2d": e(F, 29, 2), "kinect": e(F, 25, 3), "theta": e(F, 85),
+            "gather": torch.tensor(SPIN2_TO_KINECTV2, dtype=torch.int32, device=dev),
+        }
+        self._plan = p
+        self._graph = None
+        return p
+
+    def _stages(self, p):
+        """The step as an ordered list of (name, thunk); each thunk enqueues one stage on the
+        current stream through the C-ABI (no allocation, no torch op)."""
+        reg, smpl, gru = self.regressor, self.regressor.smpl, self.encoder.gru
+        rk, sk = reg._prepare(), smpl._prepare()
+        if not (smpl.extra and smpl.kinectv2):
+            raise L.GaitLibraryError("GaitHead emits the Kinect-25 set; SMPL.extra and SMPL.kinectv2 must be True")
+        S, T, F, V = p["S"], p["T"], p["F"], p["V"]
+        H = gru.hidden_size
+        ptr, call, st = L.ptr, L.call, L.stream_ptr
+        state = p["state"].data_ptr()
+        betas, cam = state + 4 * 144, state + 4 * 154
+        return [
+            ("gru", lambda: call(
+                "gait_gru_layer", ptr(p["x"]), H, ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), ptr(gru.bias_ih_l0),
+                ptr(gru.bias_hh_l0), None, ptr(p["y_raw"]), H, ptr(p["x"]), H, ptr(p["enc"]), H, None, S, T, H, H, 0,
+                ptr(p["ws"]), p["gru_bytes"], st())),
+            ("regressor", lambda: call(
+                "gait_hmr_regressor", ptr(p["enc"]), H, ptr(rk["W1x"]), ptr(rk["W1s"]), ptr(rk["b1"]), ptr(rk["W2"]),
+                ptr(rk["b2"]), ptr(rk["Wd"]), ptr(rk["bd"]), ptr(rk["init"]), 1, self.n_iter, ptr(p["state"]), F,
+                rk["din"], rk["dh"], ptr(p["ws"]), p["hmr_bytes"], st())),
+            ("rot6d", lambda: call(
+                "gait_rot6d_to_rotmat", state, 24, _STATE_LD, ptr(p["rotmat"]), F * 24, 1e-6, st())),
+            ("pose_chain", lambda: call(
+                "gait_smpl_pose_chain", ptr(p["rotmat"]), betas, _STATE_LD, ptr(sk["J_template"]),
+                ptr(sk["J_shapedirs"]), ptr(sk["parents"]), ptr(p["A"]), ptr(p["Jp"]), ptr(p["coef"]), F, st())),
+            ("blend", lambda: call(
+                "gait_smpl_blend", ptr(p["coef"]), ptr(sk["basis_t"]), ptr(p["v_posed"]), F, 3 * V, st())),
+            ("lbs", lambda: call(
+                "gait_smpl_lbs", ptr(p["v_posed"]), ptr(p["A"]), ptr(sk["lbs_weights"]), ptr(p["verts"]), F, V, st())),
+            ("joint_regress", lambda: call(
+                "gait_joint_regress", ptr(p["verts"]), ptr(sk["extra_thorax"]), ptr(p["extra"]), F, V, 1, st())),
+            ("joints", lambda: call(
+                "gait_joints_assemble", ptr(p["Jp"]), ptr(p["verts"]), V, ptr(sk["landmarks"]), sk["n_landmarks"],
+                ptr(p["extra"]), 1, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD, 5000., 224., 112.,
+                ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st())),
+            ("theta", lambda: call(
+                "gait_pack_theta", ptr(p["rotmat"]), cam, _STATE_LD, betas, _STATE_LD, ptr(p["theta"]), F, st())),
+        ]
+
+    def _launch(self, p):
+        """Enqueue one step on the current stream."""
+        for _, fn in self._stages(p):
+            fn()
+
+    @torch.no_grad()
+    def profile_stages(self, iters: int = 20, flush=None):
+        """Per-stage device time (ms, mean over `iters`) with CUDA events on the launching stream and
+        the number of kernel launches each stage makes.  `flush()` (e.g. an L2 flush) runs before
+        every timed stage, outside the event pair."""
+        p = self._plan
+        stages = self._stages(p)
+        self._launch(p)
+        torch.cuda.synchronize()
+        res = {}
+        for name, fn in stages:
+            tot, n0 = 0.0, L.launch_count()
+            for _ in range(iters):
+                if flush is not None:
+                    flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                b.synchronize()
+                tot += a.elapsed_time(b)
+            res[name] = {"ms": tot / iters, "launches": (L.launch_count() - n0) // iters}
+        return res
+
+    def capture(self, S: int, T: int):
+        """Plan buffers for (S,T) and capture one step into a CUDA graph."""
+        p = self.plan(S, T)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._launch(p)                      # warm-up outside capture (lazy module loading)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        n0 = L.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch(p)
+        self.launches_per_step = L.launch_count() - n0
+        self._graph = g
+        return g
+
+    def outputs(self):
+        p = self._plan
+        S, T = p["S"], p["T"]
+        v = lambda t: t.view(S, T, *t.shape[1:])
+        out = {"theta": v(p["theta"]), "kp_2d": v(p["kp2d"]), "kp_3d": v(p["joints"]), "rotmat": v(p["rotmat"]),
+               "kinect25": v(p["kinect"])}
+        if self.write_mesh:
+            out["verts"] = v(p["verts"])
+        return out
+
+    @torch.no_grad()
+    def step(self):
+        """Run one step on the planned input buffer `self.input` (graph replay if captured)."""
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._launch(self._plan)
+
+    @property
+    def input(self) -> torch.Tensor:
+        return self._plan["x"]
+
+    @torch.no_grad()
+    def forward(self, features: torch.Tensor):
+        """features (S,T,2048) FP32 CUDA -> dict of (S,T,...) tensors (views of the planned buffers:
+        valid until the next call)."""
+        features = L.f32(features, "features")
+        if features.dim() != 3:
+            raise ValueError(f"features must be (S,T,{self.encoder.input_size}), got {tuple(features.shape)}")
+        S, T, _ = features.shape
+        if self._plan is None or (self._plan["S"], self._plan["T"]) != (S, T):
+            self.plan(S, T)
+        self._plan["x"].copy_(features)
+        self.step()
+        return self.outputs()
