@@ -126,19 +126,34 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
  * warp per frame, parent transforms exchanged by warp shuffle level by level.
  * R (F,24,3,3); betas (F,10) frame stride ldb; J_template (24,3) = J_regressor.v_template;
  * J_shapedirs (24,3,10) = J_regressor.shapedirs; parents int32[24] (parents[0] = -1).
- * A (F,24,12): rows of the 3x4 skinning transform with the rest joint removed;
- * J_posed (F,24,3); coef (F,GAIT_BLEND_LD) optional: [R[1:]-I (207) | betas (10) | 1 | 0..]. */
+ * A (F,24,12) optional: rows of the 3x4 skinning transform with the rest joint removed;
+ * J_posed (F,24,3); coef (F,GAIT_BLEND_LD) optional: [R[1:]-I (207) | betas (10) | 1 | 0..];
+ * Aop optional (gait_smpl_lbs_aop_bytes(F) bytes): the same transforms as the tensor-core LBS
+ * operand (TF32 hi/lo split, UMMA core-matrix layout, one blob per 8 frames).  A or Aop required. */
 int gait_smpl_pose_chain(const float* R, const float* betas, int64_t ldb, const float* J_template,
                          const float* J_shapedirs, const int32_t* parents, float* A, float* J_posed,
-                         float* coef, int64_t F, gait_stream_t stream);
+                         float* coef, float* Aop, int64_t F, gait_stream_t stream);
 /* Blend shapes (smplx lbs.blend_shapes + pose offsets): v_posed (F,3V) = coef (F,224) . basis_t^T,
- * basis_t (3V,224) = [posedirs^T | shapedirs | v_template | 0]. */
-int gait_smpl_blend(const float* coef, const float* basis_t, float* v_posed, int64_t F, int64_t V3,
+ * basis_t (3V,224) = [posedirs^T | shapedirs | v_template | 0]; v_posed row stride ldv >= 3V. */
+int gait_smpl_blend(const float* coef, const float* basis_t, float* v_posed, int64_t ldv, int64_t F, int64_t V3,
                     gait_stream_t stream);
 /* Linear blend skinning (last two lines of smplx lbs): verts[f,v] = (sum_j W[v,j] A[f,j]) [v_posed;1].
- * v_posed (F,V,3); A (F,24,12); lbs_weights (V,24); verts (F,V,3). */
-int gait_smpl_lbs(const float* v_posed, const float* A, const float* lbs_weights, float* verts, int64_t F,
-                  int64_t V, gait_stream_t stream);
+ * v_posed (F,V,3) with frame stride ldv; A (F,24,12); lbs_weights (V,24); verts (F,V,3).  SIMT FP32. */
+int gait_smpl_lbs(const float* v_posed, int64_t ldv, const float* A, const float* lbs_weights, float* verts,
+                  int64_t F, int64_t V, gait_stream_t stream);
+/* The same skinning with the W.A contraction on tcgen05 tensor cores (FP32-accurate split TF32),
+ * TMA bulk copies of pre-arranged operands, 128 vertices x 8 frames per CTA:
+ *   Wpack  = gait_smpl_lbs_pack(lbs_weights)  (gait_smpl_lbs_pack_bytes(V) bytes, once per model)
+ *   Aop    = the pose-chain kernel's tensor operand output
+ *   v_posed rows padded: ldv >= 384*ceil(V/128), ldv % 4 == 0 (rows are bulk-copied 1536 B at a time)
+ *   jx (V) optional: one joint-regressor row (the MPII thorax row of J_regressor_extra); its dot
+ *   product with the skinned vertices is emitted as per-vertex-tile partial sums
+ *   jx_partial (ceil(V/128), F, 3), summed by gait_joints_assemble (extra_parts = ceil(V/128)). */
+size_t gait_smpl_lbs_pack_bytes(int64_t V);
+int gait_smpl_lbs_pack(const float* lbs_weights, float* packed, int64_t V, gait_stream_t stream);
+size_t gait_smpl_lbs_aop_bytes(int64_t F);
+int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                     float* verts, float* jx_partial, int64_t F, int64_t V, gait_stream_t stream);
 /* vertices2joints (smplx lbs; lib/models/smpl.py:113, pare.py:70-76, spin.py:279-282):
  * out (F,Rj,3) = Jreg (Rj,V) . verts (F,V,3). */
 int gait_joint_regress(const float* verts, const float* Jreg, float* out, int64_t F, int64_t V, int Rj,
@@ -146,12 +161,14 @@ int gait_joint_regress(const float* verts, const float* Jreg, float* out, int64_
 /* Joint assembly (smplx VertexJointSelector + smpl.py:114-121) with optional projection
  * (smpl.py:176-186 / geometry.py:412-425) and Kinect-25 gather (kp_utils.py:26-36).
  * Virtual joint v: v<24 -> J_posed; 24<=v<24+n_landmarks -> verts[landmark[v-24]];
- * else -> extra[v-24-n_landmarks] (extra (F,n_extra,3)).  joint_map int32[J] picks virtual joints.
+ * else -> extra[v-24-n_landmarks], extra (extra_parts, F, n_extra, 3) summed over its leading axis
+ * (parts extra_part_stride floats apart; 1 part for a complete regression).  joint_map int32[J] picks virtual joints.
  * joints (F,J,3); kp2d (F,J,2) optional (needs cam (F,3), frame stride ldcam):
  *   t = [tx, ty, 2 f/(res s + 1e-9)], kp2d = f (X+t).xy/(X+t).z / kp2d_divisor;
  * gather int32[n_gather] + gathered (F,n_gather,3) optional (entry -1 writes zeros). */
 int gait_joints_assemble(const float* J_posed, const float* verts, int64_t V, const int32_t* landmarks,
-                         int n_landmarks, const float* extra, int n_extra, const int32_t* joint_map, int J,
+                         int n_landmarks, const float* extra, int n_extra, int extra_parts, int64_t extra_part_stride,
+                         const int32_t* joint_map, int J,
                          float* joints, const float* cam, int64_t ldcam, float focal_length, float img_res,
                          float kp2d_divisor, float* kp2d, const int32_t* gather, int n_gather,
                          float* gathered, int64_t F, gait_stream_t stream);

@@ -39,11 +39,15 @@ _SIGS = {
     "gait_relu": [P, P, I64, P],
     "gait_hmr_workspace_bytes": [I64, I64],
     "gait_hmr_regressor": [P, I64, P, P, P, P, P, P, P, P, I64, I32, P, I64, I64, I64, P, SZ, P],
-    "gait_smpl_pose_chain": [P, P, I64, P, P, P, P, P, P, I64, P],
-    "gait_smpl_blend": [P, P, P, I64, I64, P],
-    "gait_smpl_lbs": [P, P, P, P, I64, I64, P],
+    "gait_smpl_pose_chain": [P, P, I64, P, P, P, P, P, P, P, I64, P],
+    "gait_smpl_blend": [P, P, P, I64, I64, I64, P],
+    "gait_smpl_lbs": [P, I64, P, P, P, I64, I64, P],
+    "gait_smpl_lbs_pack_bytes": [I64],
+    "gait_smpl_lbs_pack": [P, P, I64, P],
+    "gait_smpl_lbs_aop_bytes": [I64],
+    "gait_smpl_lbs_tc": [P, I64, P, P, P, P, P, I64, I64, P],
     "gait_joint_regress": [P, P, P, I64, I64, I32, P],
-    "gait_joints_assemble": [P, P, I64, P, I32, P, I32, P, I32, P, P, I64, F32, F32, F32, P, P, I32, P, I64, P],
+    "gait_joints_assemble": [P, P, I64, P, I32, P, I32, I32, I64, P, I32, P, P, I64, F32, F32, F32, P, P, I32, P, I64, P],
     "gait_gather_joints": [P, I32, P, I32, P, I64, P],
     "gait_pack_theta": [P, P, I64, P, I64, P, I64, P],
 }
@@ -53,6 +57,8 @@ _RESTYPES = {
     "gait_launch_count": I64,
     "gait_gru_workspace_bytes": SZ,
     "gait_hmr_workspace_bytes": SZ,
+    "gait_smpl_lbs_pack_bytes": SZ,
+    "gait_smpl_lbs_aop_bytes": SZ,
 }
 EXPORTS = tuple(_SIGS)
 

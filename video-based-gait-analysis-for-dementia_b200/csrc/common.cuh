@@ -58,4 +58,14 @@ int linear_launch(const float* A, int64_t lda, const float* W, int64_t ldw, cons
                   const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                   cudaStream_t stream);
 
+int linear_simt_launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                       const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                       cudaStream_t stream);
+// tcgen05 split-TF32 path (linear_tc.cu)
+bool linear_tc_eligible(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int64_t N, int64_t K);
+int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* Cin,
+                     int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int splits,
+                     int64_t split_stride, cudaStream_t stream);
+int linear_path();
+
 }  // namespace gait

@@ -4,16 +4,20 @@
 //
 // Input projection for all S*T frames is one GEMM; the recurrence is T steps of
 // (S,H).(H,3H) plus a fused gate kernel that also emits the TemporalEncoder residual sum.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gait {
+
+constexpr int kGruMaxSplits = 4;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // gi: (S*T, 3H) input projection incl. b_ih; gh: (S, 3H) hidden projection incl. b_hh, or NULL at
 // the first step with h0 == NULL (then gh == b_hh).
-__global__ void gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
-                                const float* __restrict__ b_hh, const float* __restrict__ hprev, int64_t ldh,
+__global__ void gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh, int gh_parts,
+                                int64_t gh_part_stride, const float* __restrict__ b_hh, const float* __restrict__ hprev, int64_t ldh,
                                 float* __restrict__ y, int64_t ldy, const float* __restrict__ resid, int64_t ldres,
                                 float* __restrict__ out, int64_t ldout, float* __restrict__ hn, int S, int T,
                                 int H, int t) {
@@ -26,6 +30,10 @@ __global__ void gru_gate_kernel(const float* __restrict__ gi, const float* __res
     if (gh) {
         const float* q = gh + (int64_t)s * 3 * H;
         hr = q[u]; hz = q[H + u]; hnn = q[2 * H + u];
+        for (int part = 1; part < gh_parts; ++part) {         // split-K partial sums of the recurrent GEMM
+            q += gh_part_stride;
+            hr += q[u]; hz += q[H + u]; hnn += q[2 * H + u];
+        }
     } else {
         hr = b_hh[u]; hz = b_hh[H + u]; hnn = b_hh[2 * H + u];
     }
@@ -59,7 +67,7 @@ int gait_relu(const float* x, float* y, int64_t n, gait_stream_t stream) {
 
 size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H) {
     if (S <= 0 || T <= 0 || H <= 0) return 0;
-    return (size_t)(S * T * 3 * H + S * 3 * H) * sizeof(float);
+    return (size_t)(S * T * 3 * H + kGruMaxSplits * S * 3 * H) * sizeof(float);
 }
 
 int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* W_hh, const float* b_ih,
@@ -83,6 +91,16 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
     // gi = x . W_ih^T + b_ih for every frame
     GAIT_TRY(linear_launch(x, ldx, W_ih, I, b_ih, nullptr, 0, gi, 3 * H, F, 3 * H, I, st));
     const dim3 block(256), grid((unsigned)ceil_div(H, 256), (unsigned)S);
+    // recurrent GEMM (S,H).(H,3H): tensor-core path with split-K so that ~all SMs get a tile
+    const int64_t hstride = T * ldy;
+    const bool tc = linear_path() != 1 && (T > 1) && linear_tc_eligible(y, hstride, W_hh, H, S, 3 * H, H);
+    int splits = 1;
+    if (tc) {
+        const int64_t tiles = ceil_div(3 * H, 128) * ceil_div(S, S <= 64 ? 64 : 128);
+        const int64_t nkb = ceil_div(H, 32);
+        splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(kGruMaxSplits, 148 / std::max<int64_t>(tiles, 1)), nkb));
+        while (splits > 1 && ceil_div(nkb, ceil_div(nkb, splits)) != splits) --splits;
+    }
     for (int64_t step = 0; step < T; ++step) {
         const int64_t t = reverse ? (T - 1 - step) : step;
         const float* hprev = nullptr;
@@ -94,11 +112,17 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
             hprev = y + tp * ldy; ldh = T * ldy;        // row s of h_{t-1} is y[s, tp, :]
         }
         const float* ghp = nullptr;
+        int parts = 1;
         if (hprev) {
-            GAIT_TRY(linear_launch(hprev, ldh, W_hh, H, b_hh, nullptr, 0, gh, 3 * H, S, 3 * H, H, st));
+            if (tc && linear_tc_eligible(hprev, ldh, W_hh, H, S, 3 * H, H)) {
+                GAIT_TRY(linear_tc_launch(hprev, ldh, W_hh, H, b_hh, nullptr, 0, gh, 3 * H, S, 3 * H, H, splits, S * 3 * H, st));
+                parts = splits;
+            } else {
+                GAIT_TRY(linear_launch(hprev, ldh, W_hh, H, b_hh, nullptr, 0, gh, 3 * H, S, 3 * H, H, st));
+            }
             ghp = gh;
         }
-        gru_gate_kernel<<<grid, block, 0, st>>>(gi, ghp, b_hh, hprev, ldh, y, ldy, resid, ldres, out, ldout,
+        gru_gate_kernel<<<grid, block, 0, st>>>(gi, ghp, parts, S * 3 * H, b_hh, hprev, ldh, y, ldy, resid, ldres, out, ldout,
                                                 (step == T - 1) ? hn : nullptr, (int)S, (int)T, (int)H, (int)t);
         GAIT_TRY(check_launch("gru_gate"));
     }

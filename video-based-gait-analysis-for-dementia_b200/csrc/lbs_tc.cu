@@ -1,0 +1,257 @@
+// Linear blend skinning on tcgen05: the dense skinning contraction of smplx lbs()
+//
+//     T[f,v] (3x4) = sum_j W[v,j] A[f,j]         (M = vertices, N = 12 x frames, K = 24 joints)
+//     verts[f,v]   = T[f,v] . [v_posed[f,v]; 1]
+//
+// is 288 FMA per (vertex, frame) against 24 bytes of HBM traffic - above the FP32 SIMT ridge, so
+// the SIMT kernel (smpl.cu) is issue-bound at ~11 % of HBM peak.  Here W.A runs on the tensor
+// cores in FP32-accurate split-TF32 form and the CUDA cores only apply T to the vertex, so the
+// kernel is bound by the v_posed / verts streams.
+//
+// One CTA = 128 vertices x 8 frames:
+//   * operands arrive as three kinds of contiguous blobs via cp.async.bulk (TMA, one mbarrier):
+//       - skin weights of the vertex tile, pre-split hi/lo and pre-arranged in the UMMA no-swizzle
+//         K-major core-matrix layout (gait_smpl_lbs_pack, once per model):          24 576 B
+//       - the 8 frames' skinning transforms, likewise hi/lo + core-matrix layout, written in that
+//         form by the kinematic-chain kernel (N = 8 frames x 12 = 96 rows, K = 24):  18 432 B
+//       - 8 rows of v_posed (128 vertices x 12 B each):                              8 x 1 536 B
+//   * one elected thread issues 9 tcgen05.mma.kind::tf32 (3 k-steps x {lo.hi, hi.lo, hi.hi}),
+//     M = 128, N = 96, accumulator in 128 TMEM columns
+//   * the 128 threads (thread = vertex = TMEM lane) read T per frame with tcgen05.ld, apply it to
+//     the vertex from smem, write the result back to smem; optional fused partial of one
+//     J_regressor_extra row (thorax) by warp shuffles; then coalesced 8-byte stores.
+//   55 KB smem and 128 TMEM columns per CTA: 4 CTAs per SM overlap load / MMA / epilogue phases.
+#include "common.cuh"
+
+namespace gait {
+namespace lbs {
+
+constexpr int NJ = 24;
+constexpr int VT = 128;                    // vertices per CTA (UMMA M)
+constexpr int FT = 8;                      // frames per CTA
+constexpr int NCOL = FT * 12;              // UMMA N = 96
+constexpr int KC = NJ / 4;                 // 16-byte K chunks = 6
+constexpr int W_PART = KC * VT * 16;       // 12 288 B (hi or lo)
+constexpr int A_PART = KC * NCOL * 16;     //  9 216 B
+constexpr int W_BLOB = 2 * W_PART;         // 24 576
+constexpr int A_BLOB = 2 * A_PART;         // 18 432
+constexpr int V_ROW = VT * 3 * 4;          //  1 536 B per frame
+constexpr int SMEM = W_BLOB + A_BLOB + FT * V_ROW + 4 * FT * 3 * 4 + 64;
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; SBO between 8-row groups, LBO between K chunks.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* o) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+    o[0] = __uint_as_float(a); o[1] = __uint_as_float(b); o[2] = __uint_as_float(c); o[3] = __uint_as_float(d);
+}
+
+// Offset (in floats) of element (row, k) inside one hi/lo part of a core-matrix blob with `rows` rows.
+__host__ __device__ __forceinline__ int blob_index(int rows, int row, int k) {
+    return ((k >> 2) * (rows >> 3) + (row >> 3)) * 32 + (row & 7) * 4 + (k & 3);
+}
+
+// Pack lbs_weights (V,24) into per-tile blobs [tile][hi|lo][kchunk][rowgroup][8][4]; rows >= V are zero.
+__global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __restrict__ out, int V, int tiles) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tiles * VT * NJ) return;
+    const int tile = i / (VT * NJ), rem = i % (VT * NJ), row = rem / NJ, k = rem % NJ;
+    const int v = tile * VT + row;
+    const float w = (v < V) ? W[(int64_t)v * NJ + k] : 0.f;
+    const float hi = rna_tf32(w), lo = rna_tf32(w - hi);
+    float* blob = out + (int64_t)tile * (W_BLOB / 4);
+    blob[blob_index(VT, row, k)] = hi;
+    blob[W_PART / 4 + blob_index(VT, row, k)] = lo;
+}
+
+template <bool HAS_JX>
+__global__ void __launch_bounds__(VT, 4)
+smpl_lbs_tc_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* __restrict__ Aop,
+                   const float* __restrict__ Wpack, const float* __restrict__ jx, float* __restrict__ verts,
+                   float* __restrict__ jx_partial, int F, int V) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + W_BLOB;
+    float* sV = reinterpret_cast<float*>(smem + W_BLOB + A_BLOB);
+    float* sJ = reinterpret_cast<float*>(smem + W_BLOB + A_BLOB + FT * V_ROW);        // [4 warps][FT][3]
+    const uint32_t bar_load = smem_u32(smem + W_BLOB + A_BLOB + FT * V_ROW + 4 * FT * 3 * 4);
+    const uint32_t bar_mma = bar_load + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + W_BLOB + A_BLOB + FT * V_ROW + 4 * FT * 3 * 4 + 16);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x, fg = blockIdx.y;
+    const int v0 = tile * VT, f0 = fg * FT;
+    const int nv = min(VT, V - v0), nf = min(FT, F - f0);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_load) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_mma) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (tid == 0) {
+        const uint32_t bytes = W_BLOB + A_BLOB + nf * V_ROW;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_load), "r"(bytes) : "memory");
+        bulk_g2s(smem_u32(sW), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, bar_load);
+        bulk_g2s(smem_u32(sA), Aop + (int64_t)fg * (A_BLOB / 4), A_BLOB, bar_load);
+        for (int f = 0; f < nf; ++f)
+            bulk_g2s(smem_u32(sV) + f * V_ROW, v_posed + (int64_t)(f0 + f) * ldv + (int64_t)v0 * 3, V_ROW, bar_load);
+        mbar_wait(bar_load, 0);
+        // D[128 x 96] = W(128 x 24) . Aop(96 x 24)^T, split-TF32: small cross terms first
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
+        constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
+        const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + W_PART, a_hi = smem_u32(sA), a_lo = a_hi + A_PART;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+            for (int ks = 0; ks < NJ / 8; ++ks) {
+                const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 2 * ks * W_LBO;
+                const uint32_t ao = (pass == 1 ? a_lo : a_hi) + 2 * ks * A_LBO;
+                umma_tf32(tmem_d, make_desc(wo, W_LBO, SBO), make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma) : "memory");
+    }
+    mbar_wait(bar_load, 0);                       // v_posed rows visible to every thread
+    mbar_wait(bar_mma, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    float jw = 0.f;
+    if (HAS_JX) jw = (tid < nv) ? jx[v0 + tid] : 0.f;
+    const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 2
+    for (int f = 0; f < nf; ++f) {
+        float t[12];
+        tmem_ld4(trow + f * 12, t);
+        tmem_ld4(trow + f * 12 + 4, t + 4);
+        tmem_ld4(trow + f * 12 + 8, t + 8);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* p = sV + f * (VT * 3) + tid * 3;
+        const float x = p[0], y = p[1], z = p[2];
+        const float ox = t[0] * x + t[1] * y + t[2] * z + t[3];
+        const float oy = t[4] * x + t[5] * y + t[6] * z + t[7];
+        const float oz = t[8] * x + t[9] * y + t[10] * z + t[11];
+        p[0] = ox; p[1] = oy; p[2] = oz;
+        if (HAS_JX) {
+            float a = jw * ox, b = jw * oy, c = jw * oz;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+                c += __shfl_xor_sync(0xffffffffu, c, o);
+            }
+            if (lane == 0) {
+                sJ[(warp * FT + f) * 3 + 0] = a; sJ[(warp * FT + f) * 3 + 1] = b; sJ[(warp * FT + f) * 3 + 2] = c;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+    // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 multiple of 8)
+    const int n2 = (nv * 3) >> 1;
+    for (int f = 0; f < nf; ++f) {
+        float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
+        const float2* src = reinterpret_cast<const float2*>(sV + f * (VT * 3));
+        for (int i = tid; i < n2; i += VT) dst[i] = src[i];
+    }
+    if (HAS_JX && tid < nf * 3) {
+        const int f = tid / 3, c = tid % 3;
+        const float s = sJ[(0 * FT + f) * 3 + c] + sJ[(1 * FT + f) * 3 + c] + sJ[(2 * FT + f) * 3 + c] + sJ[(3 * FT + f) * 3 + c];
+        jx_partial[((int64_t)tile * F + f0 + f) * 3 + c] = s;
+    }
+}
+
+}  // namespace lbs
+}  // namespace gait
+
+using namespace gait;
+
+extern "C" {
+
+size_t gait_smpl_lbs_pack_bytes(int64_t V) {
+    return V <= 0 ? 0 : (size_t)ceil_div(V, lbs::VT) * lbs::W_BLOB;
+}
+
+int gait_smpl_lbs_pack(const float* lbs_weights, float* packed, int64_t V, gait_stream_t stream) {
+    GAIT_REQUIRE(V >= 0, "smpl_lbs_pack: negative V");
+    if (V == 0) return GAIT_OK;
+    GAIT_REQUIRE(lbs_weights && packed, "smpl_lbs_pack: null pointer");
+    const int tiles = (int)ceil_div(V, lbs::VT);
+    const int n = tiles * lbs::VT * lbs::NJ;
+    lbs::lbs_pack_weights_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(lbs_weights, packed, (int)V, tiles);
+    return check_launch("smpl_lbs_pack");
+}
+
+size_t gait_smpl_lbs_aop_bytes(int64_t F) {
+    return F <= 0 ? 0 : (size_t)ceil_div(F, lbs::FT) * lbs::A_BLOB;
+}
+
+int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                     float* verts, float* jx_partial, int64_t F, int64_t V, gait_stream_t stream) {
+    GAIT_REQUIRE(F >= 0 && V >= 0, "smpl_lbs_tc: negative size");
+    if (F == 0 || V == 0) return GAIT_OK;
+    GAIT_REQUIRE(v_posed && Aop && Wpack && verts, "smpl_lbs_tc: null pointer");
+    GAIT_REQUIRE((jx == nullptr) == (jx_partial == nullptr), "smpl_lbs_tc: jx and jx_partial go together");
+    GAIT_REQUIRE((V & 1) == 0 && aligned8(verts), "smpl_lbs_tc: V must be even and verts 8-byte aligned");
+    const int64_t tiles = ceil_div(V, lbs::VT);
+    GAIT_REQUIRE(ldv >= tiles * lbs::VT * 3 && (ldv & 3) == 0 && aligned16(v_posed),
+                 "smpl_lbs_tc: v_posed rows must be padded to 384*ceil(V/128) floats (ldv %% 4 == 0, 16-byte aligned)");
+    GAIT_REQUIRE(aligned16(Aop) && aligned16(Wpack), "smpl_lbs_tc: operand blobs must be 16-byte aligned");
+    GAIT_REQUIRE(F < (1ll << 31) && V < (1ll << 31) && ceil_div(F, lbs::FT) < 65536, "smpl_lbs_tc: size too large");
+    static bool attr = false;
+    if (!attr) {
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM));
+        attr = true;
+    }
+    dim3 grid((unsigned)tiles, (unsigned)ceil_div(F, lbs::FT));
+    if (jx)
+        lbs::smpl_lbs_tc_kernel<true><<<grid, lbs::VT, lbs::SMEM, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V);
+    else
+        lbs::smpl_lbs_tc_kernel<false><<<grid, lbs::VT, lbs::SMEM, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V);
+    return check_launch("smpl_lbs_tc");
+}
+
+}  // extern "C"

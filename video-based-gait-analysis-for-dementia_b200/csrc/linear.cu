@@ -4,6 +4,9 @@
 // double-buffered shared-memory GEMM for "TN" operands (both A and W are K-major, which is how
 // torch.nn.Linear / nn.GRU store weights and activations).  It serves the shapes the tensor-core
 // path (linear_tc.cu: tcgen05 split-TF32) does not take: small M, odd K, unaligned strides.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace gait {
@@ -178,7 +181,19 @@ int linear_launch(const float* A, int64_t lda, const float* W, int64_t ldw, cons
     GAIT_REQUIRE(M > 0 && N > 0 && K > 0, "linear: sizes must be positive");
     GAIT_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "linear: size exceeds int32");
     GAIT_REQUIRE(lda >= K && ldw >= K && ldc >= N && (Cin == nullptr || ldcin >= N), "linear: stride smaller than row");
+    if (linear_path() != 1 && linear_tc_eligible(A, lda, W, ldw, M, N, K))
+        return linear_tc_launch(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, 1, 0, stream);
     return linear_simt_launch(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, stream);
+}
+
+// 0 = choose by shape (default), 1 = force the SIMT FP32 kernel (GAITB200_LINEAR=simt; A/B testing)
+int linear_path() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GAITB200_LINEAR");
+        mode = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+    }
+    return mode;
 }
 
 }  // namespace gait

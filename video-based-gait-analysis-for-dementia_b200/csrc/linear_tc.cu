@@ -1,0 +1,392 @@
+// Tensor-core path of gait_linear: FP32-accurate split-TF32 ("3xTF32") GEMM on tcgen05.
+//
+//   D[p,q] = sum_k P[p,k] Q[q,k]      P: 128-row tile (UMMA M = 128 TMEM lanes), Q: BN-row tile
+//
+// Both operands are K-major FP32 in global memory (torch Linear / GRU layout).  Per k-block of 32
+// floats (= one 128-byte swizzle span) the pipeline is
+//
+//   TMA producer (1 thread)      cp.async.bulk.tensor 2D, SWIZZLE_128B  -> raw P/Q tiles in smem
+//   converter warps (4 warps)    x -> hi = rna_tf32(x) (in place), lo = x - hi (second tile);
+//                                elementwise, so the TMA swizzle pattern is preserved
+//   MMA issuer (1 thread)        per 8-wide k-step three tcgen05.mma.kind::tf32 into one TMEM
+//                                accumulator: P_lo.Q_hi + P_hi.Q_lo + P_hi.Q_hi
+//   promotion warps (4 warps)     every 2 k-blocks: tcgen05.ld 32x32b of the TMEM partial sum, added
+//                                (round-to-nearest) into FP32 registers; two TMEM buffers alternate.
+//                                Final: +bias +Cin -> coalesced global stores
+//
+// with mbarrier full/converted/empty rings (3 stages) and a TMEM-full barrier.  Dropped term:
+// P_lo.Q_lo ~ 2^-22 relative.  The same kernel serves C = A.W^T (P = A) and the transposed
+// form (P = W, Q = A) that keeps 128 TMEM lanes busy when A has few rows (GRU recurrence,
+// S = 64); split-K over blockIdx.z writes partial sums that the consumer adds.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace gait {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int STAGES = 3;
+constexpr int DRAIN_KB = 2;               // k-blocks accumulated in TMEM between promotions to FP32 registers
+constexpr int THREADS = 320;              // warp0 TMA, warp1 MMA/TMEM, warps 2-5 convert, warps 6-9 promote + epilogue
+constexpr int NCONV = 128;
+constexpr int NDRAIN = 128;
+
+template <int BN>
+struct Cfg {
+    static constexpr int P_TILE = BM * BK * 4;
+    static constexpr int Q_TILE = BN * BK * 4;
+    static constexpr int STAGE = 2 * P_TILE + 2 * Q_TILE;     // [P hi][P lo][Q hi][Q lo]
+    static constexpr int STAGING = 4 * 32 * 33 * 4;
+    static constexpr int BAR_BYTES = 128;
+    static constexpr int SMEM = STAGES * STAGE + STAGING + BAR_BYTES + 1024;   // +1024 alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;                  // two accumulator buffers
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms, 1024 B apart).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+// barrier slots (8 B each)
+enum : int { B_FULL = 0, B_CONV = 3, B_EMPTY = 6, B_ACC_FULL = 9, B_ACC_EMPTY = 11 };
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
+                   const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
+                   int P_rows, int Q_rows, int K, int transposed, int kb_per_split, int64_t split_stride, int mode) {
+    using cfg = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + STAGES * cfg::STAGE + cfg::STAGING;
+    auto BAR = [&](int i) { return bars + 8u * i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * cfg::STAGE + cfg::STAGING + 112);
+    float* staging = reinterpret_cast<float*>(gbase + STAGES * cfg::STAGE);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * BM, q0 = blockIdx.y * BN;
+    const int nkb_total = (K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int nkb = min(kb_per_split, nkb_total - kb0);
+    const int drain_kb = (mode == 2) ? (1 << 30) : DRAIN_KB;          // mode 2 (debug): never promote
+    const int nchunks = (nkb + drain_kb - 1) / drain_kb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(BAR(B_FULL + s), 1);
+            mbar_init(BAR(B_CONV + s), NCONV);
+            mbar_init(BAR(B_EMPTY + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(BAR(B_ACC_FULL + b), 1);
+            mbar_init(BAR(B_ACC_EMPTY + b), NDRAIN);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+                const uint32_t st = base + s * cfg::STAGE;
+                mbar_arrive_expect_tx(BAR(B_FULL + s), cfg::P_TILE + cfg::Q_TILE);
+                tma_load_2d(st, &tmP, (kb0 + kb) * BK, p0, BAR(B_FULL + s));
+                tma_load_2d(st + 2 * cfg::P_TILE, &tmQ, (kb0 + kb) * BK, q0, BAR(B_FULL + s));
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                const int chunk = kb / drain_kb, buf = chunk & 1;
+                const bool chunk_start = (kb % drain_kb) == 0;
+                if (chunk_start && chunk >= 2) mbar_wait(BAR(B_ACC_EMPTY + buf), ((chunk >> 1) - 1) & 1);
+                mbar_wait(BAR(B_CONV + s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_d + (uint32_t)(buf * BN);
+                const uint32_t st = base + s * cfg::STAGE;
+                const uint64_t p_hi = make_sdesc(st), p_lo = make_sdesc(st + cfg::P_TILE);
+                const uint64_t q_hi = make_sdesc(st + 2 * cfg::P_TILE), q_lo = make_sdesc(st + 2 * cfg::P_TILE + cfg::Q_TILE);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);       // 8 floats = 32 bytes along K inside the swizzle span
+                    const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
+                    if (mode == 1) {                                        // debug: plain TF32
+                        umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, first);
+                    } else {
+                        umma_tf32(acc, p_lo + adv, q_hi + adv, idesc, first);
+                        umma_tf32(acc, p_hi + adv, q_lo + adv, idesc, 1u);
+                        umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, 1u);
+                    }
+                }
+                umma_commit(BAR(B_EMPTY + s));                              // frees the stage when the MMAs retire
+                if ((kb % drain_kb) == drain_kb - 1 || kb == nkb - 1) umma_commit(BAR(B_ACC_FULL + buf));
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------------------------------------------------------- converters: x -> (tf32 hi, lo)
+        const int ct = threadIdx.x - 64;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(BAR(B_FULL + s), ph);
+            uint8_t* st = gbase + s * cfg::STAGE;
+            auto convert = [&](uint8_t* hi, uint8_t* lo, int chunks) {
+#pragma unroll 4
+                for (int c = ct; c < chunks; c += NCONV) {
+                    float4 v = *reinterpret_cast<float4*>(hi + c * 16);
+                    float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+                    float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    *reinterpret_cast<float4*>(hi + c * 16) = h;
+                    *reinterpret_cast<float4*>(lo + c * 16) = l;
+                }
+            };
+            convert(st, st + cfg::P_TILE, cfg::P_TILE / 16);
+            convert(st + 2 * cfg::P_TILE, st + 2 * cfg::P_TILE + cfg::Q_TILE, cfg::Q_TILE / 16);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_CONV + s));
+        }
+    } else {
+        // ---------------------------------------------------------------- promotion + epilogue
+        // The tensor core adds into its FP32 accumulator with truncation, so error grows linearly
+        // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every DRAIN_KB
+        // k-blocks the TMEM partial sum is therefore added (round-to-nearest) into FP32 registers.
+        const int quad = warp & 3;                                  // this warp owns TMEM lanes 32*quad .. +31
+        float accr[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) accr[j] = 0.f;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(BAR(B_ACC_FULL + buf), (chunk >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) accr[c * 32 + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(BAR(B_ACC_EMPTY + buf));
+        }
+        const int prow = p0 + quad * 32 + lane;
+        const bool first_split = blockIdx.z == 0;
+        float* Cz = C + blockIdx.z * split_stride;
+        float* stg = staging + quad * 32 * 33;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+            if (transposed) {
+                // D row = output column: lanes run along the contiguous output dimension
+                if (prow < P_rows) {
+                    const float bv = (bias && first_split) ? bias[prow] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int qrow = q0 + c * 32 + j;
+                        if (qrow < Q_rows) {
+                            float o = accr[c * 32 + j] + bv;
+                            if (Cin && first_split) o += Cin[(int64_t)qrow * ldcin + prow];
+                            Cz[(int64_t)qrow * ldc + prow] = o;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = accr[c * 32 + j];
+                __syncwarp();
+                const int col = q0 + c * 32 + lane;
+                if (col < Q_rows) {
+                    const float bv = (bias && first_split) ? bias[col] : 0.f;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = p0 + quad * 32 + rr;
+                        if (row < P_rows) {
+                            float o = stg[rr * 33 + lane] + bv;
+                            if (Cin && first_split) o += Cin[(int64_t)row * ldcin + col];
+                            Cz[(int64_t)row * ldc + col] = o;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("linear(tc): cuTensorMapEncodeTiled entry point unavailable");
+        return GAIT_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("linear(tc): cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, (long long)rows,
+                  (long long)K, (long long)ld);
+        return GAIT_ERR_CUDA;
+    }
+    return GAIT_OK;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const float* bias, const float* Cin, int64_t ldcin,
+                  float* C, int64_t ldc, int P_rows, int Q_rows, int K, int transposed, int splits, int64_t split_stride,
+                  cudaStream_t stream) {
+    using cfg = Cfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GAIT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
+        attr_set = true;
+    }
+    const int nkb = (K + BK - 1) / BK;
+    const int kb_per_split = (nkb + splits - 1) / splits;
+    const int real_splits = (nkb + kb_per_split - 1) / kb_per_split;
+    if (real_splits != splits) {
+        set_error("linear(tc): K=%d cannot be cut into %d non-empty splits", K, splits);
+        return GAIT_ERR_INVALID;
+    }
+    dim3 grid((unsigned)ceil_div(P_rows, BM), (unsigned)ceil_div(Q_rows, BN), (unsigned)splits);
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GAITB200_TC_MODE");
+        mode = e ? atoi(e) : 0;
+    }
+    gemm_tf32x3_kernel<BN><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
+                                                                transposed, kb_per_split, split_stride, mode);
+    return check_launch("linear(tf32x3 tcgen05)");
+}
+
+}  // namespace tc
+
+bool linear_tc_eligible(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int64_t N, int64_t K) {
+    return ((lda & 3) == 0) && ((ldw & 3) == 0) && aligned16(A) && aligned16(W) && K >= 32 && N >= 64 &&
+           (M >= 16 || N >= 512);
+}
+
+// splits > 1: C must hold `splits` partial results `split_stride` floats apart; bias/Cin go into split 0.
+int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* Cin,
+                     int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int splits,
+                     int64_t split_stride, cudaStream_t stream) {
+    using namespace tc;
+    CUtensorMap tmP, tmQ;
+    // few activation rows: put the weight rows on the 128 TMEM lanes, activations on the N side
+    const bool transposed = M <= 64 || (M < 128 && N >= 128);
+    if (transposed) {
+        const int bn = (M <= 64) ? 64 : 128;
+        GAIT_TRY(make_map(&tmP, W, N, K, ldw, BM));
+        GAIT_TRY(make_map(&tmQ, A, M, K, lda, bn));
+        if (bn == 64)
+            return launch<64>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
+        return launch<128>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
+    }
+    const int bn = (ceil_div(M, BM) * ceil_div(N, 128) < 120 && N > 64) ? 64 : 128;
+    GAIT_TRY(make_map(&tmP, A, M, K, lda, BM));
+    GAIT_TRY(make_map(&tmQ, W, N, K, ldw, bn));
+    if (bn == 64)
+        return launch<64>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
+    return launch<128>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
+}
+
+}  // namespace gait

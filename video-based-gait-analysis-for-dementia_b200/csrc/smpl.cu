@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(kChainWarps * 32)
 smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ betas, int64_t ldb,
                        const float* __restrict__ J_template, const float* __restrict__ J_shapedirs,
                        const int32_t* __restrict__ parents, float* __restrict__ A, float* __restrict__ J_posed,
-                       float* __restrict__ coef, int64_t F) {
+                       float* __restrict__ coef, float* __restrict__ Aop, int64_t F) {
     __shared__ int s_parent[32];
     __shared__ int s_depth[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,11 +98,35 @@ smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ be
     }
     if (!active) return;
     // A = G - pad(G @ [J;0]): translation column loses the rotated rest joint
-    float* a = A + (f * NJ + j) * 12;
+    float av[12];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float gj = g[i * 3 + 0] * Jr[0] + g[i * 3 + 1] * Jr[1] + g[i * 3 + 2] * Jr[2];
-        reinterpret_cast<float4*>(a)[i] = make_float4(g[i * 3 + 0], g[i * 3 + 1], g[i * 3 + 2], t[i] - gj);
+        av[i * 4 + 0] = g[i * 3 + 0]; av[i * 4 + 1] = g[i * 3 + 1]; av[i * 4 + 2] = g[i * 3 + 2]; av[i * 4 + 3] = t[i] - gj;
+    }
+    if (A) {
+        float* a = A + (f * NJ + j) * 12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            reinterpret_cast<float4*>(a)[i] = make_float4(av[i * 4], av[i * 4 + 1], av[i * 4 + 2], av[i * 4 + 3]);
+    }
+    if (Aop) {
+        // tensor-core LBS operand (lbs_tc.cu): per 8-frame group a blob [hi|lo][kchunk][rowgroup][8][4] with
+        // row n = (f % 8) * 12 + c, k = joint; values pre-split into TF32 hi/lo.
+        float* blob = Aop + (f >> 3) * (2 * 6 * 96 * 4);
+        const int fl = (int)(f & 7);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const int n = fl * 12 + c;
+            const int idx = ((j >> 2) * 12 + (n >> 3)) * 32 + (n & 7) * 4 + (j & 3);
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(av[c]));
+            const float hi = __uint_as_float(hb);
+            uint32_t lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(av[c] - hi));
+            blob[idx] = hi;
+            blob[6 * 96 * 4 + idx] = __uint_as_float(lb);
+        }
     }
     float* jp = J_posed + (f * NJ + j) * 3;
     jp[0] = t[0]; jp[1] = t[1]; jp[2] = t[2];
@@ -133,7 +157,7 @@ constexpr int LBS_VT = 128;     // vertices per CTA (= threads)
 constexpr int LBS_FT = 8;       // frames per CTA
 
 __global__ void __launch_bounds__(LBS_VT)
-smpl_lbs_kernel(const float* __restrict__ v_posed, const float* __restrict__ A, const float* __restrict__ W,
+smpl_lbs_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* __restrict__ A, const float* __restrict__ W,
                 float* __restrict__ verts, int F, int V) {
     __shared__ __align__(16) float sA[LBS_FT][NJ * 12];
     __shared__ float sW[LBS_VT][NJ + 1];
@@ -154,11 +178,11 @@ smpl_lbs_kernel(const float* __restrict__ v_posed, const float* __restrict__ A, 
     for (int i = tid; i < nv * NJ; i += LBS_VT) sW[i / NJ][i % NJ] = W[(int64_t)v0 * NJ + i];
     // stage v_posed tile: per frame nv*3 contiguous floats (8-byte aligned: V*3*4 and v0*12 are multiples of 8)
     for (int f = 0; f < nf; ++f) {
-        const float2* src = reinterpret_cast<const float2*>(v_posed + ((int64_t)(f0 + f) * V + v0) * 3);
+        const float2* src = reinterpret_cast<const float2*>(v_posed + (int64_t)(f0 + f) * ldv + (int64_t)v0 * 3);
         float2* dst = reinterpret_cast<float2*>(&sV[f][0]);
         const int n2 = (nv * 3) >> 1;
         for (int i = tid; i < n2; i += LBS_VT) dst[i] = src[i];
-        if (((nv * 3) & 1) && tid == 0) sV[f][nv * 3 - 1] = v_posed[((int64_t)(f0 + f) * V + v0) * 3 + nv * 3 - 1];
+        if (((nv * 3) & 1) && tid == 0) sV[f][nv * 3 - 1] = v_posed[(int64_t)(f0 + f) * ldv + (int64_t)v0 * 3 + nv * 3 - 1];
     }
     __syncthreads();
 
@@ -278,20 +302,30 @@ joint_regress_kernel(const float* __restrict__ verts, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // Joint assembly + projection + Kinect-25 gather: one thread per (frame, output joint).
 // ------------------------------------------------------------------------------------------
+struct ExtraJoints {
+    const float* data;       // (parts, F, n_extra, 3): partial sums over vertex tiles, or one complete part
+    int n_extra, parts;
+    int64_t part_stride;
+};
+
 __device__ __forceinline__ void fetch_virtual_joint(int v, int64_t f, const float* __restrict__ J_posed,
                                                     const float* __restrict__ verts, int64_t V,
                                                     const int32_t* __restrict__ landmarks, int n_landmarks,
-                                                    const float* __restrict__ extra, int n_extra, float* o) {
-    const float* p;
-    if (v < NJ) p = J_posed + (f * NJ + v) * 3;
-    else if (v < NJ + n_landmarks) p = verts + (f * V + landmarks[v - NJ]) * 3;
-    else p = extra + (f * n_extra + (v - NJ - n_landmarks)) * 3;
+                                                    const ExtraJoints& ex, float* o) {
+    if (v >= NJ + n_landmarks) {
+        const float* p = ex.data + (f * ex.n_extra + (v - NJ - n_landmarks)) * 3;
+        float x = 0.f, y = 0.f, z = 0.f;
+        for (int q = 0; q < ex.parts; ++q, p += ex.part_stride) { x += p[0]; y += p[1]; z += p[2]; }
+        o[0] = x; o[1] = y; o[2] = z;
+        return;
+    }
+    const float* p = (v < NJ) ? J_posed + (f * NJ + v) * 3 : verts + (f * V + landmarks[v - NJ]) * 3;
     o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
 }
 
 __global__ void joints_assemble_kernel(const float* __restrict__ J_posed, const float* __restrict__ verts, int64_t V,
                                        const int32_t* __restrict__ landmarks, int n_landmarks,
-                                       const float* __restrict__ extra, int n_extra,
+                                       ExtraJoints ex,
                                        const int32_t* __restrict__ joint_map, int J, float* __restrict__ joints,
                                        const float* __restrict__ cam, int64_t ldcam, float focal, float res,
                                        float divisor, float* __restrict__ kp2d, const int32_t* __restrict__ gather,
@@ -303,7 +337,7 @@ __global__ void joints_assemble_kernel(const float* __restrict__ J_posed, const 
     const int k = (int)(i % per);
     float p[3];
     if (k < J) {
-        fetch_virtual_joint(joint_map[k], f, J_posed, verts, V, landmarks, n_landmarks, extra, n_extra, p);
+        fetch_virtual_joint(joint_map[k], f, J_posed, verts, V, landmarks, n_landmarks, ex, p);
         float* o = joints + (f * J + k) * 3;
         o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
         if (kp2d) {
@@ -314,7 +348,7 @@ __global__ void joints_assemble_kernel(const float* __restrict__ J_posed, const 
         }
     } else {
         const int g = gather[k - J];
-        if (g >= 0) fetch_virtual_joint(joint_map[g], f, J_posed, verts, V, landmarks, n_landmarks, extra, n_extra, p);
+        if (g >= 0) fetch_virtual_joint(joint_map[g], f, J_posed, verts, V, landmarks, n_landmarks, ex, p);
         else { p[0] = 0.f; p[1] = 0.f; p[2] = 0.f; }
         float* o = gathered + (f * n_gather + (k - J)) * 3;
         o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
@@ -352,36 +386,36 @@ extern "C" {
 
 int gait_smpl_pose_chain(const float* R, const float* betas, int64_t ldb, const float* J_template,
                          const float* J_shapedirs, const int32_t* parents, float* A, float* J_posed,
-                         float* coef, int64_t F, gait_stream_t stream) {
+                         float* coef, float* Aop, int64_t F, gait_stream_t stream) {
     GAIT_REQUIRE(F >= 0, "smpl_pose_chain: negative F");
     if (F == 0) return GAIT_OK;
-    GAIT_REQUIRE(R && betas && J_template && J_shapedirs && parents && A && J_posed, "smpl_pose_chain: null pointer");
+    GAIT_REQUIRE(R && betas && J_template && J_shapedirs && parents && J_posed && (A || Aop), "smpl_pose_chain: null pointer");
     GAIT_REQUIRE(ldb >= NB, "smpl_pose_chain: ldb < 10");
-    GAIT_REQUIRE(aligned16(A), "smpl_pose_chain: A must be 16-byte aligned");
+    GAIT_REQUIRE(A == nullptr || aligned16(A), "smpl_pose_chain: A must be 16-byte aligned");
     smpl_pose_chain_kernel<<<(unsigned)ceil_div(F, kChainWarps), kChainWarps * 32, 0, as_stream(stream)>>>(
-        R, betas, ldb, J_template, J_shapedirs, parents, A, J_posed, coef, F);
+        R, betas, ldb, J_template, J_shapedirs, parents, A, J_posed, coef, Aop, F);
     return check_launch("smpl_pose_chain");
 }
 
-int gait_smpl_blend(const float* coef, const float* basis_t, float* v_posed, int64_t F, int64_t V3,
+int gait_smpl_blend(const float* coef, const float* basis_t, float* v_posed, int64_t ldv, int64_t F, int64_t V3,
                     gait_stream_t stream) {
     GAIT_REQUIRE(F >= 0 && V3 >= 0, "smpl_blend: negative size");
     if (F == 0 || V3 == 0) return GAIT_OK;
-    GAIT_REQUIRE(coef && basis_t && v_posed, "smpl_blend: null pointer");
-    return linear_launch(coef, GAIT_BLEND_LD, basis_t, GAIT_BLEND_LD, nullptr, nullptr, 0, v_posed, V3, F, V3,
+    GAIT_REQUIRE(coef && basis_t && v_posed && ldv >= V3, "smpl_blend: null pointer or ldv < 3V");
+    return linear_launch(coef, GAIT_BLEND_LD, basis_t, GAIT_BLEND_LD, nullptr, nullptr, 0, v_posed, ldv, F, V3,
                          GAIT_BLEND_LD, as_stream(stream));
 }
 
-int gait_smpl_lbs(const float* v_posed, const float* A, const float* lbs_weights, float* verts, int64_t F,
-                  int64_t V, gait_stream_t stream) {
+int gait_smpl_lbs(const float* v_posed, int64_t ldv, const float* A, const float* lbs_weights, float* verts,
+                  int64_t F, int64_t V, gait_stream_t stream) {
     GAIT_REQUIRE(F >= 0 && V >= 0, "smpl_lbs: negative size");
     if (F == 0 || V == 0) return GAIT_OK;
     GAIT_REQUIRE(v_posed && A && lbs_weights && verts, "smpl_lbs: null pointer");
     GAIT_REQUIRE(aligned16(A) && aligned8(v_posed) && aligned8(verts), "smpl_lbs: misaligned pointer");
-    GAIT_REQUIRE((V & 1) == 0, "smpl_lbs: V must be even (8-byte row alignment of the vertex streams)");
+    GAIT_REQUIRE((V & 1) == 0 && (ldv & 1) == 0 && ldv >= 3 * V, "smpl_lbs: V and ldv must be even (8-byte row alignment), ldv >= 3V");
     GAIT_REQUIRE(F < (1ll << 31) && V < (1ll << 31) && ceil_div(F, LBS_FT) < 65536, "smpl_lbs: size too large");
     dim3 grid((unsigned)ceil_div(V, LBS_VT), (unsigned)ceil_div(F, LBS_FT));
-    smpl_lbs_kernel<<<grid, LBS_VT, 0, as_stream(stream)>>>(v_posed, A, lbs_weights, verts, (int)F, (int)V);
+    smpl_lbs_kernel<<<grid, LBS_VT, 0, as_stream(stream)>>>(v_posed, ldv, A, lbs_weights, verts, (int)F, (int)V);
     return check_launch("smpl_lbs");
 }
 
@@ -397,20 +431,21 @@ int gait_joint_regress(const float* verts, const float* Jreg, float* out, int64_
 }
 
 int gait_joints_assemble(const float* J_posed, const float* verts, int64_t V, const int32_t* landmarks,
-                         int n_landmarks, const float* extra, int n_extra, const int32_t* joint_map, int J,
-                         float* joints, const float* cam, int64_t ldcam, float focal_length, float img_res,
+                         int n_landmarks, const float* extra, int n_extra, int extra_parts, int64_t extra_part_stride,
+                         const int32_t* joint_map, int J, float* joints, const float* cam, int64_t ldcam, float focal_length, float img_res,
                          float kp2d_divisor, float* kp2d, const int32_t* gather, int n_gather,
                          float* gathered, int64_t F, gait_stream_t stream) {
     GAIT_REQUIRE(F >= 0 && J >= 0 && n_gather >= 0 && n_landmarks >= 0 && n_extra >= 0, "joints_assemble: negative size");
     if (F == 0 || J + n_gather == 0) return GAIT_OK;
     GAIT_REQUIRE(J_posed && joint_map && joints, "joints_assemble: null pointer");
     GAIT_REQUIRE(n_landmarks == 0 || (verts && landmarks), "joints_assemble: landmarks need verts");
-    GAIT_REQUIRE(n_extra == 0 || extra, "joints_assemble: n_extra > 0 needs extra");
+    GAIT_REQUIRE(n_extra == 0 || (extra && extra_parts >= 1), "joints_assemble: n_extra > 0 needs extra and extra_parts >= 1");
     GAIT_REQUIRE(kp2d == nullptr || (cam && ldcam >= 3 && aligned8(kp2d)), "joints_assemble: kp2d needs cam");
     GAIT_REQUIRE(n_gather == 0 || (gather && gathered), "joints_assemble: gather needs output");
     const int64_t n = F * (J + n_gather);
     joints_assemble_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
-        J_posed, verts, V, landmarks, n_landmarks, extra, n_extra, joint_map, J, joints, cam, ldcam, focal_length,
+        J_posed, verts, V, landmarks, n_landmarks, ExtraJoints{extra, n_extra, extra_parts, extra_part_stride}, joint_map, J,
+        joints, cam, ldcam, focal_length,
         img_res, kp2d_divisor, kp2d, gather, n_gather, gathered, F);
     return check_launch("joints_assemble");
 }
