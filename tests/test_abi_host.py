@@ -54,7 +54,8 @@ def test_version_and_error_strings(lib):
 def test_argument_validation_without_gpu(lib):
     # empty problems succeed without touching the device
     assert lib.gait_rot6d_to_rotmat(None, 1, 6, None, 0, 1e-6, None) == 0
-    assert lib.gait_smpl_lbs(None, None, None, None, 0, 6890, None) == 0
+    assert lib.gait_smpl_lbs(None, 0, None, None, None, 0, 6890, None) == 0
+    assert lib.gait_smpl_lbs_tc(None, 0, None, None, None, None, None, 0, 6890, None) == 0
     assert lib.gait_linear(None, 0, None, 0, None, None, 0, None, 0, 0, 16, 16, None) == 0
     assert lib.gait_gru_layer(None, 0, None, None, None, None, None, None, 0, None, 0, None, 0, None,
                               0, 16, 8, 8, 0, None, 0, None) == 0
@@ -64,8 +65,11 @@ def test_argument_validation_without_gpu(lib):
     assert lib.gait_rot6d_to_rotmat(None, 1, 6, None, -1, 1e-6, None) == -1
     assert lib.gait_rotmat_to_quaternion(C.c_void_p(16), 5, C.c_void_p(16), 1, 1e-6, None) == -1
     assert lib.gait_batch_rodrigues(C.c_void_p(16), C.c_void_p(16), 1, 7, None) == -1
-    assert lib.gait_smpl_lbs(C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 6891, None) == -1
-    assert lib.gait_smpl_lbs(C.c_void_p(20), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 6890, None) == -1
+    assert lib.gait_smpl_lbs(C.c_void_p(16), 3 * 6892, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 6891, None) == -1
+    assert lib.gait_smpl_lbs(C.c_void_p(20), 20670, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, 6890, None) == -1
+    # tensor-core LBS: v_posed rows must be padded to whole 128-vertex tiles
+    assert lib.gait_smpl_lbs_tc(C.c_void_p(16), 20670, C.c_void_p(16), C.c_void_p(16), None, C.c_void_p(16), None, 1, 6890, None) == -1
+    assert lib.gait_smpl_lbs_pack_bytes(6890) == 54 * 24576 and lib.gait_smpl_lbs_aop_bytes(1024) == 128 * 18432
     assert lib.gait_linear(C.c_void_p(16), 4, C.c_void_p(16), 8, None, None, 0, C.c_void_p(16), 8, 2, 8, 8, None) == -1
     assert lib.gait_gru_workspace_bytes(64, 16, 2048) == (64 * 16 * 6144 + 4 * 64 * 6144) * 4
     assert lib.gait_hmr_workspace_bytes(1024, 1024) == 3 * 1024 * 1024 * 4

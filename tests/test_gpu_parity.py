@@ -180,6 +180,65 @@ def test_smpl_vs_oracle(variant, F, lib_loaded):
     assert maxerr(out.vertices, ref.vertices) <= TOL_V and maxerr(out.joints, ref.joints) <= TOL_V
 
 
+@pytest.mark.parametrize("variant,F", [("sparse", 1), ("dense", 8), ("sparse", 13), ("dense", 70)])
+def test_lbs_kernels_vs_oracle(variant, F, lib_loaded):
+    """Both skinning kernels (SIMT FP32 and tcgen05 split-TF32) against the oracle's dense
+    W.A + apply (smplx lbs, last two lines), plus the fused thorax partial sums."""
+    L = lib_loaded
+    from oracle import geometry as OG
+    from oracle import smplx_lbs as OL
+    data = synthetic.make_smpl_data(seed=5, variant=variant)
+    V = 6890
+    rot6d, betas, _ = synthetic.make_pose_inputs(F, seed=100 + F, noise=0.5)
+    R = OG.rot6d_to_rotmat(rot6d).view(F, 24, 3, 3)
+    J = 0.3 * torch.randn(F, 24, 3, generator=torch.Generator().manual_seed(F))
+    _, A = OL.batch_rigid_transform(R, J, T(data["parents"]))
+    g = torch.Generator().manual_seed(1)
+    vp = torch.randn(F, V, 3, generator=g) * 0.4
+    W = T(data["lbs_weights"])
+    Tm = torch.matmul(W.unsqueeze(0).expand(F, -1, -1), A.view(F, 24, 16)).view(F, V, 4, 4)
+    ref = torch.matmul(Tm, torch.cat([vp, torch.ones(F, V, 1)], 2).unsqueeze(-1))[:, :, :3, 0]
+    A12 = A[:, :, :3, :].reshape(F, 24, 12).contiguous().cuda()
+    st = L.stream_ptr()
+    # SIMT kernel, contiguous v_posed
+    vpd, Wd = vp.cuda(), W.cuda()
+    out = torch.empty(F, V, 3, device="cuda")
+    L.call("gait_smpl_lbs", vpd.data_ptr(), 3 * V, A12.data_ptr(), Wd.data_ptr(), out.data_ptr(), F, V, st)
+    assert maxerr(out, ref) <= 1e-5
+    # tensor-core kernel: packed weights, padded v_posed rows, Aop produced by the chain kernel
+    lib = L.load()
+    ldv = 384 * 54
+    vpp = torch.zeros(F, ldv, device="cuda")
+    vpp[:, :3 * V] = vpd.reshape(F, -1)
+    wpack = torch.empty(lib.gait_smpl_lbs_pack_bytes(V) // 4, device="cuda")
+    L.call("gait_smpl_lbs_pack", Wd.data_ptr(), wpack.data_ptr(), V, st)
+    # chain kernel with J_shapedirs = 0 and J_template = J[0]: reproduce A for frame-constant joints
+    Jc = J[:1].expand(F, -1, -1).contiguous()
+    _, Ac = OL.batch_rigid_transform(R, Jc, T(data["parents"]))
+    aop = torch.full((lib.gait_smpl_lbs_aop_bytes(F) // 4,), float("nan"), device="cuda")
+    Jp = torch.empty(F, 24, 3, device="cuda")
+    A_out = torch.empty(F, 24, 12, device="cuda")
+    Rd, bd, Jt = R.cuda(), betas.cuda(), Jc[0].contiguous().cuda()          # keep the operands alive
+    Jsd, par = torch.zeros(24, 3, 10, device="cuda"), T(data["parents"]).to(torch.int32).cuda()
+    L.call("gait_smpl_pose_chain", Rd.data_ptr(), bd.data_ptr(), 10, Jt.data_ptr(), Jsd.data_ptr(), par.data_ptr(),
+           A_out.data_ptr(), Jp.data_ptr(), None, aop.data_ptr(), F, st)
+    torch.cuda.synchronize()
+    assert maxerr(A_out, Ac[:, :, :3, :].reshape(F, 24, 12)) <= 1e-5
+    Tc = torch.matmul(W.unsqueeze(0).expand(F, -1, -1), Ac.view(F, 24, 16)).view(F, V, 4, 4)
+    refc = torch.matmul(Tc, torch.cat([vp, torch.ones(F, V, 1)], 2).unsqueeze(-1))[:, :, :3, 0]
+    jx = T(data["J_regressor_extra"][5]).cuda()
+    part = torch.empty(54, F, 3, device="cuda")
+    out2 = torch.empty(F, V, 3, device="cuda")
+    L.call("gait_smpl_lbs_tc", vpp.data_ptr(), ldv, aop.data_ptr(), wpack.data_ptr(), jx.data_ptr(), out2.data_ptr(),
+           part.data_ptr(), F, V, st)
+    assert maxerr(out2, refc) <= 1e-5
+    thorax = torch.einsum('v,fvc->fc', T(data["J_regressor_extra"][5]), refc)
+    assert maxerr(part.sum(0), thorax) <= 1e-5
+    out3 = torch.empty(F, V, 3, device="cuda")
+    L.call("gait_smpl_lbs_tc", vpp.data_ptr(), ldv, aop.data_ptr(), wpack.data_ptr(), None, out3.data_ptr(), None, F, V, st)
+    assert torch.equal(out3, out2)
+
+
 def test_smpl_wrapper_vs_reference_golden(golden, smpl_data, lib_loaded):
     from gaitb200.smpl import SMPL, SMPLHead
     g = golden("smpl_wrapper")

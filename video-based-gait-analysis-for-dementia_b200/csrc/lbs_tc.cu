@@ -8,7 +8,7 @@
 // cores in FP32-accurate split-TF32 form and the CUDA cores only apply T to the vertex, so the
 // kernel is bound by the v_posed / verts streams.
 //
-// One CTA = 128 vertices x 8 frames:
+// One work item = 128 vertices x 8 frames (a CTA loops over up to 4 items of one vertex tile):
 //   * operands arrive as three kinds of contiguous blobs via cp.async.bulk (TMA, one mbarrier):
 //       - skin weights of the vertex tile, pre-split hi/lo and pre-arranged in the UMMA no-swizzle
 //         K-major core-matrix layout (gait_smpl_lbs_pack, once per model):          24 576 B
@@ -20,7 +20,9 @@
 //   * the 128 threads (thread = vertex = TMEM lane) read T per frame with tcgen05.ld, apply it to
 //     the vertex from smem, write the result back to smem; optional fused partial of one
 //     J_regressor_extra row (thorax) by warp shuffles; then coalesced 8-byte stores.
-//   55 KB smem and 128 TMEM columns per CTA: 4 CTAs per SM overlap load / MMA / epilogue phases.
+//   The weight blob stays in smem for the CTA's lifetime; the per-group operands and the TMEM
+//   accumulator are double-buffered, so TMA loads and MMAs of group g+1 run under the epilogue and
+//   stores of group g.  86 KB smem + 256 TMEM columns per CTA: 2 CTAs per SM.
 #include "common.cuh"
 
 namespace gait {
@@ -36,8 +38,6 @@ constexpr int A_PART = KC * NCOL * 16;     //  9 216 B
 constexpr int W_BLOB = 2 * W_PART;         // 24 576
 constexpr int A_BLOB = 2 * A_PART;         // 18 432
 constexpr int V_ROW = VT * 3 * 4;          //  1 536 B per frame
-constexpr int SMEM = W_BLOB + A_BLOB + FT * V_ROW + 4 * FT * 3 * 4 + 64;
-constexpr int TMEM_COLS = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float rna_tf32(float x) {
@@ -70,12 +70,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* o) {
-    uint32_t a, b, c, d;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
-    o[0] = __uint_as_float(a); o[1] = __uint_as_float(b); o[2] = __uint_as_float(c); o[3] = __uint_as_float(d);
-}
 
 // Offset (in floats) of element (row, k) inside one hi/lo part of a core-matrix blob with `rows` rows.
 __host__ __device__ __forceinline__ int blob_index(int rows, int row, int k) {
@@ -95,111 +89,175 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
     blob[W_PART / 4 + blob_index(VT, row, k)] = lo;
 }
 
+// One CTA = one 128-vertex tile x up to GPC groups of 8 frames.  The weight blob is loaded once; the
+// per-group operands (transform blob + 8 v_posed rows) are double-buffered so the next group's TMA
+// loads and MMAs run under the current group's epilogue and stores.
+constexpr int GPC = 4;                                   // frame groups per CTA
+constexpr int STAGE = A_BLOB + FT * V_ROW;               // 30 720 B
+constexpr int OFF_STAGE = W_BLOB;
+constexpr int OFF_JX = OFF_STAGE + 2 * STAGE;            // 128 floats of the fused regressor row
+constexpr int OFF_BAR = OFF_JX + VT * 4;
+constexpr int SMEM2 = OFF_BAR + 64;
+constexpr int TMEM_COLS2 = 256;                          // two 96-column accumulators
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* o) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 12; ++i) o[i] = __uint_as_float(r[i]);
+}
+
 template <bool HAS_JX>
-__global__ void __launch_bounds__(VT, 4)
+__global__ void __launch_bounds__(VT, 2)
 smpl_lbs_tc_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* __restrict__ Aop,
                    const float* __restrict__ Wpack, const float* __restrict__ jx, float* __restrict__ verts,
                    float* __restrict__ jx_partial, int F, int V) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sW = smem;
-    uint8_t* sA = smem + W_BLOB;
-    float* sV = reinterpret_cast<float*>(smem + W_BLOB + A_BLOB);
-    float* sJ = reinterpret_cast<float*>(smem + W_BLOB + A_BLOB + FT * V_ROW);        // [4 warps][FT][3]
-    const uint32_t bar_load = smem_u32(smem + W_BLOB + A_BLOB + FT * V_ROW + 4 * FT * 3 * 4);
-    const uint32_t bar_mma = bar_load + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + W_BLOB + A_BLOB + FT * V_ROW + 4 * FT * 3 * 4 + 16);
+    float* sJx = reinterpret_cast<float*>(smem + OFF_JX);
+    const uint32_t bar0 = smem_u32(smem + OFF_BAR);
+    auto FULL = [&](int b) { return bar0 + 8u * b; };
+    auto MMA = [&](int b) { return bar0 + 16u + 8u * b; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, fg = blockIdx.y;
-    const int v0 = tile * VT, f0 = fg * FT;
-    const int nv = min(VT, V - v0), nf = min(FT, F - f0);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int total_groups = (F + FT - 1) / FT;
+    const int g0 = blockIdx.y * GPC;
+    const int ng = min(GPC, total_groups - g0);
+    const int v0 = tile * VT;
+    const int nv = min(VT, V - v0);
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_load) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_mma) : "memory");
+        for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * b) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS2) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (HAS_JX) sJx[tid] = (tid < nv) ? jx[v0 + tid] : 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (tid == 0) {
-        const uint32_t bytes = W_BLOB + A_BLOB + nf * V_ROW;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_load), "r"(bytes) : "memory");
-        bulk_g2s(smem_u32(sW), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, bar_load);
-        bulk_g2s(smem_u32(sA), Aop + (int64_t)fg * (A_BLOB / 4), A_BLOB, bar_load);
+    // ---- helpers run by thread 0 only
+    auto issue_loads = [&](int g, bool with_w) {
+        const int b = g & 1;
+        const int nf = min(FT, F - (g0 + g) * FT);
+        const uint32_t st = smem_u32(smem + OFF_STAGE + b * STAGE);
+        const uint32_t bytes = (with_w ? W_BLOB : 0) + A_BLOB + nf * V_ROW;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(b)), "r"(bytes) : "memory");
+        if (with_w) bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, FULL(b));
+        bulk_g2s(st, Aop + (int64_t)(g0 + g) * (A_BLOB / 4), A_BLOB, FULL(b));
         for (int f = 0; f < nf; ++f)
-            bulk_g2s(smem_u32(sV) + f * V_ROW, v_posed + (int64_t)(f0 + f) * ldv + (int64_t)v0 * 3, V_ROW, bar_load);
-        mbar_wait(bar_load, 0);
+            bulk_g2s(st + A_BLOB + f * V_ROW, v_posed + (int64_t)((g0 + g) * FT + f) * ldv + (int64_t)v0 * 3, V_ROW, FULL(b));
+    };
+    auto issue_mma = [&](int g) {
         // D[128 x 96] = W(128 x 24) . Aop(96 x 24)^T, split-TF32: small cross terms first
+        const int b = g & 1;
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
         constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
-        const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + W_PART, a_hi = smem_u32(sA), a_lo = a_hi + A_PART;
+        const uint32_t w_hi = smem_u32(smem), w_lo = w_hi + W_PART;
+        const uint32_t a_hi = smem_u32(smem + OFF_STAGE + b * STAGE), a_lo = a_hi + A_PART;
+        const uint32_t acc = tmem_d + (uint32_t)(b * NCOL);
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
             for (int ks = 0; ks < NJ / 8; ++ks) {
                 const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 2 * ks * W_LBO;
                 const uint32_t ao = (pass == 1 ? a_lo : a_hi) + 2 * ks * A_LBO;
-                umma_tf32(tmem_d, make_desc(wo, W_LBO, SBO), make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
+                umma_tf32(acc, make_desc(wo, W_LBO, SBO), make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
             }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma) : "memory");
-    }
-    mbar_wait(bar_load, 0);                       // v_posed rows visible to every thread
-    mbar_wait(bar_mma, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMA(b)) : "memory");
+    };
 
-    float jw = 0.f;
-    if (HAS_JX) jw = (tid < nv) ? jx[v0 + tid] : 0.f;
+    if (tid == 0) {
+        issue_loads(0, true);
+        if (ng > 1) issue_loads(1, false);
+        mbar_wait(FULL(0), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_mma(0);
+    }
+
     const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
+    for (int g = 0; g < ng; ++g) {
+        const int b = g & 1;
+        const uint32_t ph = (g >> 1) & 1;
+        const int f0 = (g0 + g) * FT;
+        const int nf = min(FT, F - f0);
+        float* sV = reinterpret_cast<float*>(smem + OFF_STAGE + b * STAGE + A_BLOB);
+        if (tid == 0 && g + 1 < ng) {                       // tensor work for the next group runs under this epilogue
+            mbar_wait(FULL(b ^ 1), ((g + 1) >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_mma(g + 1);
+        }
+        mbar_wait(FULL(b), ph);                             // v_posed rows visible to every thread
+        mbar_wait(MMA(b), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 2
-    for (int f = 0; f < nf; ++f) {
-        float t[12];
-        tmem_ld4(trow + f * 12, t);
-        tmem_ld4(trow + f * 12 + 4, t + 4);
-        tmem_ld4(trow + f * 12 + 8, t + 8);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* p = sV + f * (VT * 3) + tid * 3;
-        const float x = p[0], y = p[1], z = p[2];
-        const float ox = t[0] * x + t[1] * y + t[2] * z + t[3];
-        const float oy = t[4] * x + t[5] * y + t[6] * z + t[7];
-        const float oz = t[8] * x + t[9] * y + t[10] * z + t[11];
-        p[0] = ox; p[1] = oy; p[2] = oz;
+        for (int f = 0; f < nf; ++f) {
+            float t[12];
+            tmem_ld16(trow + b * NCOL + f * 12, t);
+            float* p = sV + f * (VT * 3) + tid * 3;
+            const float x = p[0], y = p[1], z = p[2];
+            p[0] = t[0] * x + t[1] * y + t[2] * z + t[3];
+            p[1] = t[4] * x + t[5] * y + t[6] * z + t[7];
+            p[2] = t[8] * x + t[9] * y + t[10] * z + t[11];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
         if (HAS_JX) {
-            float a = jw * ox, b = jw * oy, c = jw * oz;
+            // partial dot product of the regressor row with this tile's skinned vertices:
+            // thread = (frame, 16-way split of the 128 vertices), then a 16-lane shuffle reduction
+            const int f = tid >> 4, part = tid & 15;
+            float a = 0.f, bb = 0.f, c = 0.f;
+            if (f < nf) {
+                const float* row = sV + f * (VT * 3);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+                for (int i = 0; i < VT / 16; ++i) {
+                    const int v = part + 16 * i;
+                    const float w = sJx[v];
+                    a = fmaf(w, row[v * 3], a); bb = fmaf(w, row[v * 3 + 1], bb); c = fmaf(w, row[v * 3 + 2], c);
+                }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
                 a += __shfl_xor_sync(0xffffffffu, a, o);
-                b += __shfl_xor_sync(0xffffffffu, b, o);
+                bb += __shfl_xor_sync(0xffffffffu, bb, o);
                 c += __shfl_xor_sync(0xffffffffu, c, o);
             }
-            if (lane == 0) {
-                sJ[(warp * FT + f) * 3 + 0] = a; sJ[(warp * FT + f) * 3 + 1] = b; sJ[(warp * FT + f) * 3 + 2] = c;
+            if (part == 0 && f < nf) {
+                float* o = jx_partial + ((int64_t)tile * F + f0 + f) * 3;
+                o[0] = a; o[1] = bb; o[2] = c;
             }
+        }
+        // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 multiple of 8)
+        const int n2 = (nv * 3) >> 1;
+#pragma unroll 2
+        for (int f = 0; f < nf; ++f) {
+            float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
+            const float2* src = reinterpret_cast<const float2*>(sV + f * (VT * 3));
+            if (tid < n2) dst[tid] = src[tid];
+            if (tid + VT < n2) dst[tid + VT] = src[tid + VT];
+        }
+        if (g + 2 < ng) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to this stage precede its TMA refill
+            __syncthreads();
+            if (tid == 0) issue_loads(g + 2, false);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
-    }
-    // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 multiple of 8)
-    const int n2 = (nv * 3) >> 1;
-    for (int f = 0; f < nf; ++f) {
-        float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
-        const float2* src = reinterpret_cast<const float2*>(sV + f * (VT * 3));
-        for (int i = tid; i < n2; i += VT) dst[i] = src[i];
-    }
-    if (HAS_JX && tid < nf * 3) {
-        const int f = tid / 3, c = tid % 3;
-        const float s = sJ[(0 * FT + f) * 3 + c] + sJ[(1 * FT + f) * 3 + c] + sJ[(2 * FT + f) * 3 + c] + sJ[(3 * FT + f) * 3 + c];
-        jx_partial[((int64_t)tile * F + f0 + f) * 3 + c] = s;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS2) : "memory");
     }
 }
 
@@ -242,15 +300,15 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
     GAIT_REQUIRE(F < (1ll << 31) && V < (1ll << 31) && ceil_div(F, lbs::FT) < 65536, "smpl_lbs_tc: size too large");
     static bool attr = false;
     if (!attr) {
-        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM));
-        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM2));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM2));
         attr = true;
     }
-    dim3 grid((unsigned)tiles, (unsigned)ceil_div(F, lbs::FT));
+    dim3 grid((unsigned)tiles, (unsigned)ceil_div(ceil_div(F, lbs::FT), lbs::GPC));
     if (jx)
-        lbs::smpl_lbs_tc_kernel<true><<<grid, lbs::VT, lbs::SMEM, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V);
+        lbs::smpl_lbs_tc_kernel<true><<<grid, lbs::VT, lbs::SMEM2, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V);
     else
-        lbs::smpl_lbs_tc_kernel<false><<<grid, lbs::VT, lbs::SMEM, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V);
+        lbs::smpl_lbs_tc_kernel<false><<<grid, lbs::VT, lbs::SMEM2, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V);
     return check_launch("smpl_lbs_tc");
 }
 

@@ -58,8 +58,10 @@ class GaitHead(nn.Module):
             "S": S, "T": T, "F": F, "V": V, "dev": dev,
             "x": e(S, T, H), "y_raw": e(S, T, H), "enc": e(S, T, H),
             "ws": e(max(gru_bytes, hmr_bytes, 4) // 4), "gru_bytes": gru_bytes, "hmr_bytes": hmr_bytes,
-            "state": e(F, _STATE_LD), "rotmat": e(F, 24, 3, 3), "A": e(F, 24, 12), "Jp": e(F, 24, 3),
-            "coef": e(F, 224), "v_posed": e(F, V, 3), "verts": e(F, V, 3), "extra": e(F, 1, 3),
+            "state": e(F, _STATE_LD), "rotmat": e(F, 24, 3, 3), "Jp": e(F, 24, 3),
+            "aop": e(lib.gait_smpl_lbs_aop_bytes(F) // 4),
+            "coef": e(F, 224), "v_posed": e(F, 384 * ((V + 127) // 128)), "verts": e(F, V, 3),
+            "extra": e((V + 127) // 128, F, 1, 3),
             "joints": e(F, 29, 3), "kp2d": e(F, 29, 2), "kinect": e(F, 25, 3), "theta": e(F, 85),
             "gather": torch.tensor(SPIN2_TO_KINECTV2, dtype=torch.int32, device=dev),
         }
@@ -92,16 +94,16 @@ class GaitHead(nn.Module):
                 "gait_rot6d_to_rotmat", state, 24, _STATE_LD, ptr(p["rotmat"]), F * 24, 1e-6, st())),
             ("pose_chain", lambda: call(
                 "gait_smpl_pose_chain", ptr(p["rotmat"]), betas, _STATE_LD, ptr(sk["J_template"]),
-                ptr(sk["J_shapedirs"]), ptr(sk["parents"]), ptr(p["A"]), ptr(p["Jp"]), ptr(p["coef"]), F, st())),
+                ptr(sk["J_shapedirs"]), ptr(sk["parents"]), None, ptr(p["Jp"]), ptr(p["coef"]), ptr(p["aop"]), F, st())),
             ("blend", lambda: call(
-                "gait_smpl_blend", ptr(p["coef"]), ptr(sk["basis_t"]), ptr(p["v_posed"]), F, 3 * V, st())),
+                "gait_smpl_blend", ptr(p["coef"]), ptr(sk["basis_t"]), ptr(p["v_posed"]), sk["ldv"], F, 3 * V, st())),
             ("lbs", lambda: call(
-                "gait_smpl_lbs", ptr(p["v_posed"]), ptr(p["A"]), ptr(sk["lbs_weights"]), ptr(p["verts"]), F, V, st())),
-            ("joint_regress", lambda: call(
-                "gait_joint_regress", ptr(p["verts"]), ptr(sk["extra_thorax"]), ptr(p["extra"]), F, V, 1, st())),
+                "gait_smpl_lbs_tc", ptr(p["v_posed"]), sk["ldv"], ptr(p["aop"]), ptr(sk["lbs_wpack"]),
+                ptr(sk["extra_thorax"]), ptr(p["verts"]), ptr(p["extra"]), F, V, st())),
             ("joints", lambda: call(
                 "gait_joints_assemble", ptr(p["Jp"]), ptr(p["verts"]), V, ptr(sk["landmarks"]), sk["n_landmarks"],
-                ptr(p["extra"]), 1, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD, 5000., 224., 112.,
+                ptr(p["extra"]), 1, sk["vtiles"], F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
+                5000., 224., 112.,
                 ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st())),
             ("theta", lambda: call(
                 "gait_pack_theta", ptr(p["rotmat"]), cam, _STATE_LD, betas, _STATE_LD, ptr(p["theta"]), F, st())),

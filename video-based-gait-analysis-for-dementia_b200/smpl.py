@@ -6,7 +6,7 @@
 (lbs.py: blend shapes, vertices2joints, Rodrigues, batch_rigid_transform, skinning;
 vertex_joint_selector.py) runs in hand-written CUDA kernels through include/gaitb200.h:
 
-    pose chain (1 warp / frame)  ->  blend GEMM  ->  LBS  ->  extra-joint regression  ->  assembly/projection
+    pose chain (1 warp / frame)  ->  blend GEMM (tcgen05)  ->  LBS (tcgen05, thorax row fused)  ->  assembly/projection
 
 There is no CPU path: inputs must be FP32 CUDA tensors.
 """
@@ -158,6 +158,9 @@ class SMPL(nn.Module):
         basis_t[:, :207] = self.posedirs.t()
         basis_t[:, 207:217] = self.shapedirs.reshape(3 * V, 10)
         basis_t[:, 217] = vt.reshape(-1)
+        lbs_w = self.lbs_weights.contiguous()
+        wpack = torch.empty(L.load().gait_smpl_lbs_pack_bytes(V) // 4, device=dev)
+        L.call("gait_smpl_lbs_pack", L.ptr(lbs_w), L.ptr(wpack), V, st)
         lm = self.vertex_joint_selector.extra_joints_idxs.to(torch.int32).contiguous()
         n_lm = lm.numel()
         i32 = lambda xs: torch.tensor(list(xs), dtype=torch.int32, device=dev)
@@ -167,7 +170,9 @@ class SMPL(nn.Module):
             "J_shapedirs": Jsd.permute(1, 2, 0).contiguous(),             # (24,3,10)
             "basis_t": basis_t,
             "parents": self.parents.to(torch.int32).contiguous(),
-            "lbs_weights": self.lbs_weights.contiguous(),
+            "lbs_weights": lbs_w,
+            "lbs_wpack": wpack,                                           # tensor-core LBS operand (lbs_tc.cu)
+            "vtiles": (V + 127) // 128, "ldv": 384 * ((V + 127) // 128),  # padded v_posed row (TMA bulk rows)
             "landmarks": lm, "n_landmarks": n_lm,
             "extra_all": self.J_regressor_extra.contiguous(),
             "extra_thorax": self.J_regressor_extra[_THORAX_ROW:_THORAX_ROW + 1].contiguous(),
@@ -191,7 +196,8 @@ class SMPL(nn.Module):
     def run(self, rotmat, betas, cam=None, focal_length=5000., img_res=224., kp2d_divisor=1.0, want_verts=True,
             gather=None):
         """rotmat (F,24,3,3), betas (F,10) -> dict(vertices, joints[, joints2d][, gathered]).
-        One pose-chain, one blend GEMM, one LBS, one joint-regression and one assembly launch."""
+        One pose-chain, one blend GEMM, one LBS (+ one joint-regression launch in the 49-joint mode)
+        and one assembly launch."""
         pk = self._prepare()
         R = L.f32(rotmat, "rotmat").reshape(-1, NUM_JOINTS, 3, 3)
         F = R.shape[0]
@@ -199,22 +205,33 @@ class SMPL(nn.Module):
         if betas.shape[0] != F:
             betas = betas.expand(F, -1).contiguous()
         dev, V, st = R.device, pk["V"], L.stream_ptr()
-        A = torch.empty(F, NUM_JOINTS, 12, device=dev)
         Jp = torch.empty(F, NUM_JOINTS, 3, device=dev)
         coef = torch.empty(F, 224, device=dev)
+        lib = L.load()
+        aop = torch.empty(lib.gait_smpl_lbs_aop_bytes(F) // 4, device=dev)
         L.call("gait_smpl_pose_chain", L.ptr(R), L.ptr(betas), betas.stride(0), L.ptr(pk["J_template"]),
-               L.ptr(pk["J_shapedirs"]), L.ptr(pk["parents"]), L.ptr(A), L.ptr(Jp), L.ptr(coef), F, st)
-        v_posed = torch.empty(F, V, 3, device=dev)
-        L.call("gait_smpl_blend", L.ptr(coef), L.ptr(pk["basis_t"]), L.ptr(v_posed), F, 3 * V, st)
+               L.ptr(pk["J_shapedirs"]), L.ptr(pk["parents"]), None, L.ptr(Jp), L.ptr(coef), L.ptr(aop), F, st)
+        ldv, vtiles = pk["ldv"], pk["vtiles"]
+        v_posed = torch.empty(F, ldv, device=dev)
+        L.call("gait_smpl_blend", L.ptr(coef), L.ptr(pk["basis_t"]), L.ptr(v_posed), ldv, F, 3 * V, st)
         verts = torch.empty(F, V, 3, device=dev)
-        L.call("gait_smpl_lbs", L.ptr(v_posed), L.ptr(A), L.ptr(pk["lbs_weights"]), L.ptr(verts), F, V, st)
-        if self.extra:
-            Jx = pk["extra_thorax"] if self.kinectv2 else pk["extra_all"]
-            jmap = pk["map_kinect"] if self.kinectv2 else pk["map_spin"]
-            extra = torch.empty(F, Jx.shape[0], 3, device=dev)
-            L.call("gait_joint_regress", L.ptr(verts), L.ptr(Jx), L.ptr(extra), F, V, Jx.shape[0], st)
+        extra, extra_parts, extra_stride = None, 1, 0
+        if self.extra and self.kinectv2:
+            # thorax row of J_regressor_extra fused into the skinning kernel as per-tile partial sums
+            jmap = pk["map_kinect"]
+            extra = torch.empty(vtiles, F, 1, 3, device=dev)
+            extra_parts, extra_stride = vtiles, F * 3
+            L.call("gait_smpl_lbs_tc", L.ptr(v_posed), ldv, L.ptr(aop), L.ptr(pk["lbs_wpack"]),
+                   L.ptr(pk["extra_thorax"]), L.ptr(verts), L.ptr(extra), F, V, st)
         else:
-            Jx, jmap, extra = None, pk["map_smplx"], None
+            L.call("gait_smpl_lbs_tc", L.ptr(v_posed), ldv, L.ptr(aop), L.ptr(pk["lbs_wpack"]), None, L.ptr(verts),
+                   None, F, V, st)
+            if self.extra:
+                Jx, jmap = pk["extra_all"], pk["map_spin"]
+                extra = torch.empty(1, F, Jx.shape[0], 3, device=dev)
+                L.call("gait_joint_regress", L.ptr(verts), L.ptr(Jx), L.ptr(extra), F, V, Jx.shape[0], st)
+            else:
+                jmap = pk["map_smplx"]
         J = jmap.numel()
         joints = torch.empty(F, J, 3, device=dev)
         kp2d = torch.empty(F, J, 2, device=dev) if cam is not None else None
@@ -224,7 +241,8 @@ class SMPL(nn.Module):
             gidx = gather.to(device=dev, dtype=torch.int32).contiguous()
             gat = torch.empty(F, gidx.numel(), 3, device=dev)
         L.call("gait_joints_assemble", L.ptr(Jp), L.ptr(verts), V, L.ptr(pk["landmarks"]), pk["n_landmarks"],
-               L.ptr(extra), 0 if extra is None else extra.shape[1], L.ptr(jmap), J, L.ptr(joints), L.ptr(camc),
+               L.ptr(extra), 0 if extra is None else extra.shape[2], extra_parts, extra_stride, L.ptr(jmap), J,
+               L.ptr(joints), L.ptr(camc),
                0 if camc is None else camc.stride(0), float(focal_length), float(img_res), float(kp2d_divisor),
                L.ptr(kp2d), L.ptr(gidx), 0 if gidx is None else gidx.numel(), L.ptr(gat), F, st)
         out = {"vertices": verts, "joints": joints}
