@@ -23,6 +23,8 @@
 //   The weight blob stays in smem for the CTA's lifetime; the per-group operands and the TMEM
 //   accumulator are double-buffered, so TMA loads and MMAs of group g+1 run under the epilogue and
 //   stores of group g.  86 KB smem + 256 TMEM columns per CTA: 2 CTAs per SM.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gait {
@@ -89,175 +91,221 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
     blob[W_PART / 4 + blob_index(VT, row, k)] = lo;
 }
 
-// One CTA = one 128-vertex tile x up to GPC groups of 8 frames.  The weight blob is loaded once; the
-// per-group operands (transform blob + 8 v_posed rows) are double-buffered so the next group's TMA
-// loads and MMAs run under the current group's epilogue and stores.
-constexpr int GPC = 4;                                   // frame groups per CTA
+// Persistent, warp-specialised kernel: one CTA per SM walks a contiguous range of work items
+// (vertex tile, 8-frame group) in tile-major order.
+//   warp 8  (1 thread)  producer : TMA loads into a 4-stage ring (transform blob + 8 v_posed rows per item),
+//                                  weight blob reloaded when the range crosses into the next vertex tile
+//   warp 9  (1 thread)  MMA      : 9 tcgen05.mma per item into TMEM buffer = stage
+//   warps 0-7           compute  : warp w owns TMEM lanes 32*(w%4).. (= vertices) and frames 4*(w/4)..+3:
+//                                  tcgen05.ld T, apply to v_posed in smem, fused regressor-row partial,
+//                                  coalesced stores, then release the stage
+// Loads run up to 3 items ahead of the epilogue, which is what hides the TMA/HBM latency.
+constexpr int NS = 4;                                    // stages = TMEM accumulator buffers
 constexpr int STAGE = A_BLOB + FT * V_ROW;               // 30 720 B
 constexpr int OFF_STAGE = W_BLOB;
-constexpr int OFF_JX = OFF_STAGE + 2 * STAGE;            // 128 floats of the fused regressor row
+constexpr int OFF_JX = OFF_STAGE + NS * STAGE;           // 128 floats of the fused regressor row
 constexpr int OFF_BAR = OFF_JX + VT * 4;
-constexpr int SMEM2 = OFF_BAR + 64;
-constexpr int TMEM_COLS2 = 256;                          // two 96-column accumulators
+constexpr int SMEM3 = OFF_BAR + 128;
+constexpr int TMEM_COLS3 = 512;                          // NS x 96 columns -> 512 (power of two)
+constexpr int NCOMPUTE = 256;
+constexpr int THREADS3 = NCOMPUTE + 64;
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* o) {
-    uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 12; ++i) o[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 template <bool HAS_JX>
-__global__ void __launch_bounds__(VT, 2)
+__global__ void __launch_bounds__(THREADS3, 1)
 smpl_lbs_tc_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* __restrict__ Aop,
                    const float* __restrict__ Wpack, const float* __restrict__ jx, float* __restrict__ verts,
-                   float* __restrict__ jx_partial, int F, int V) {
+                   float* __restrict__ jx_partial, int F, int V, int groups, int n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* sJx = reinterpret_cast<float*>(smem + OFF_JX);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
-    auto FULL = [&](int b) { return bar0 + 8u * b; };
-    auto MMA = [&](int b) { return bar0 + 16u + 8u * b; };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 32);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };               // TMA landed (tx count)
+    auto MMAD = [&](int s) { return bar0 + 32u + 8u * s; };         // accumulator ready
+    auto EMPTY = [&](int s) { return bar0 + 64u + 8u * s; };        // compute warps done with the stage
+    const uint32_t WFULL = bar0 + 96u;                              // weight blob landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int tile = blockIdx.x;
-    const int total_groups = (F + FT - 1) / FT;
-    const int g0 = blockIdx.y * GPC;
-    const int ng = min(GPC, total_groups - g0);
-    const int v0 = tile * VT;
-    const int nv = min(VT, V - v0);
+    // contiguous, balanced item range of this CTA; item = tile * groups + group
+    const int item_lo = (int)(((int64_t)n_items * blockIdx.x) / gridDim.x);
+    const int item_hi = (int)(((int64_t)n_items * (blockIdx.x + 1)) / gridDim.x);
 
     if (tid == 0) {
-        for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * b) : "memory");
+        for (int s = 0; s < NS; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(FULL(s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(s)), "r"(NCOMPUTE) : "memory");
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WFULL) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS2) : "memory");
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS3) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (HAS_JX) sJx[tid] = (tid < nv) ? jx[v0 + tid] : 0.f;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    // ---- helpers run by thread 0 only
-    auto issue_loads = [&](int g, bool with_w) {
-        const int b = g & 1;
-        const int nf = min(FT, F - (g0 + g) * FT);
-        const uint32_t st = smem_u32(smem + OFF_STAGE + b * STAGE);
-        const uint32_t bytes = (with_w ? W_BLOB : 0) + A_BLOB + nf * V_ROW;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(b)), "r"(bytes) : "memory");
-        if (with_w) bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, FULL(b));
-        bulk_g2s(st, Aop + (int64_t)(g0 + g) * (A_BLOB / 4), A_BLOB, FULL(b));
-        for (int f = 0; f < nf; ++f)
-            bulk_g2s(st + A_BLOB + f * V_ROW, v_posed + (int64_t)((g0 + g) * FT + f) * ldv + (int64_t)v0 * 3, V_ROW, FULL(b));
-    };
-    auto issue_mma = [&](int g) {
-        // D[128 x 96] = W(128 x 24) . Aop(96 x 24)^T, split-TF32: small cross terms first
-        const int b = g & 1;
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
-        constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
-        const uint32_t w_hi = smem_u32(smem), w_lo = w_hi + W_PART;
-        const uint32_t a_hi = smem_u32(smem + OFF_STAGE + b * STAGE), a_lo = a_hi + A_PART;
-        const uint32_t acc = tmem_d + (uint32_t)(b * NCOL);
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll
-            for (int ks = 0; ks < NJ / 8; ++ks) {
-                const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 2 * ks * W_LBO;
-                const uint32_t ao = (pass == 1 ? a_lo : a_hi) + 2 * ks * A_LBO;
-                umma_tf32(acc, make_desc(wo, W_LBO, SBO), make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
+    if (warp == 8) {
+        // ---------------------------------------------------------------- producer
+        if (tid == NCOMPUTE) {
+            int cur_tile = -1, wuse = 0;
+            for (int item = item_lo; item < item_hi; ++item) {
+                const int n = item - item_lo, s = n % NS;
+                const int tile = item / groups, g = item % groups;
+                if (n >= NS) mbar_wait(EMPTY(s), ((n / NS) - 1) & 1);
+                if (tile != cur_tile) {
+                    // the previous tile's MMAs (which read the weight blob) must have retired: its last item is
+                    // item-1, whose stage is released only after its accumulator was consumed
+                    if (cur_tile >= 0) {
+                        const int pn = n - 1;
+                        mbar_wait(EMPTY(pn % NS), (pn / NS) & 1);
+                    }
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(WFULL), "r"((uint32_t)W_BLOB) : "memory");
+                    bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, WFULL);
+                    cur_tile = tile;
+                    ++wuse;
+                }
+                const int f0 = g * FT, nf = min(FT, F - f0);
+                const uint32_t st = smem_u32(smem + OFF_STAGE + s * STAGE);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)(A_BLOB + nf * V_ROW)) : "memory");
+                bulk_g2s(st, Aop + (int64_t)g * (A_BLOB / 4), A_BLOB, FULL(s));
+                for (int f = 0; f < nf; ++f)
+                    bulk_g2s(st + A_BLOB + f * V_ROW, v_posed + (int64_t)(f0 + f) * ldv + (int64_t)tile * (VT * 3), V_ROW, FULL(s));
             }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMA(b)) : "memory");
-    };
-
-    if (tid == 0) {
-        issue_loads(0, true);
-        if (ng > 1) issue_loads(1, false);
-        mbar_wait(FULL(0), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_mma(0);
-    }
-
-    const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int g = 0; g < ng; ++g) {
-        const int b = g & 1;
-        const uint32_t ph = (g >> 1) & 1;
-        const int f0 = (g0 + g) * FT;
-        const int nf = min(FT, F - f0);
-        float* sV = reinterpret_cast<float*>(smem + OFF_STAGE + b * STAGE + A_BLOB);
-        if (tid == 0 && g + 1 < ng) {                       // tensor work for the next group runs under this epilogue
-            mbar_wait(FULL(b ^ 1), ((g + 1) >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_mma(g + 1);
-        }
-        mbar_wait(FULL(b), ph);                             // v_posed rows visible to every thread
-        mbar_wait(MMA(b), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 2
-        for (int f = 0; f < nf; ++f) {
-            float t[12];
-            tmem_ld16(trow + b * NCOL + f * 12, t);
-            float* p = sV + f * (VT * 3) + tid * 3;
-            const float x = p[0], y = p[1], z = p[2];
-            p[0] = t[0] * x + t[1] * y + t[2] * z + t[3];
-            p[1] = t[4] * x + t[5] * y + t[6] * z + t[7];
-            p[2] = t[8] * x + t[9] * y + t[10] * z + t[11];
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (HAS_JX) {
-            // partial dot product of the regressor row with this tile's skinned vertices:
-            // thread = (frame, 16-way split of the 128 vertices), then a 16-lane shuffle reduction
-            const int f = tid >> 4, part = tid & 15;
-            float a = 0.f, bb = 0.f, c = 0.f;
-            if (f < nf) {
-                const float* row = sV + f * (VT * 3);
+    } else if (warp == 9) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (tid == NCOMPUTE + 32) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
+            constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
+            const uint32_t w_hi = smem_u32(smem), w_lo = w_hi + W_PART;
+            int cur_tile = -1, wuse = 0;
+            for (int item = item_lo; item < item_hi; ++item) {
+                const int n = item - item_lo, s = n % NS;
+                const int tile = item / groups;
+                if (tile != cur_tile) {
+                    mbar_wait(WFULL, wuse & 1);
+                    cur_tile = tile;
+                    ++wuse;
+                }
+                mbar_wait(FULL(s), (n / NS) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + OFF_STAGE + s * STAGE), a_lo = a_hi + A_PART;
+                const uint32_t acc = tmem_d + (uint32_t)(s * NCOL);
+                // D[128 x 96] = W(128 x 24) . Aop(96 x 24)^T, split-TF32: small cross terms first
 #pragma unroll
-                for (int i = 0; i < VT / 16; ++i) {
-                    const int v = part + 16 * i;
-                    const float w = sJx[v];
-                    a = fmaf(w, row[v * 3], a); bb = fmaf(w, row[v * 3 + 1], bb); c = fmaf(w, row[v * 3 + 2], c);
+                for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                    for (int ks = 0; ks < NJ / 8; ++ks) {
+                        const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 2 * ks * W_LBO;
+                        const uint32_t ao = (pass == 1 ? a_lo : a_hi) + 2 * ks * A_LBO;
+                        umma_tf32(acc, make_desc(wo, W_LBO, SBO), make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(s)) : "memory");
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- compute warps
+        const int quad = warp & 3, fh = warp >> 2;                 // TMEM lane quarter, frame half (frames 4*fh..+3)
+        const int vl = quad * 32 + (tid & 31);                     // vertex within the tile = TMEM lane
+        int cur_tile = -1;
+        for (int item = item_lo; item < item_hi; ++item) {
+            const int n = item - item_lo, s = n % NS;
+            const uint32_t ph = (n / NS) & 1;
+            const int tile = item / groups, g = item % groups;
+            const int v0 = tile * VT, nv = min(VT, V - v0);
+            const int f0 = g * FT, nf = min(FT, F - f0);
+            float* sV = reinterpret_cast<float*>(smem + OFF_STAGE + s * STAGE + A_BLOB);
+            if (HAS_JX && tile != cur_tile) {
+                asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory");     // previous tile's partial pass finished
+                if (tid < VT) sJx[tid] = (tid < nv) ? jx[v0 + tid] : 0.f;
+                cur_tile = tile;
+            }
+            mbar_wait(FULL(s), ph);                                // v_posed rows visible
+            mbar_wait(MMAD(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+                // 4 frames x 12 accumulator columns of this vertex, and its 4 v_posed entries, fetched up front
+                uint32_t t[48];
+                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * NCOL + fh * 48);
+                tmem_ld16_nowait(taddr, t);
+                tmem_ld16_nowait(taddr + 16, t + 16);
+                tmem_ld16_nowait(taddr + 32, t + 32);
+                float* p = sV + (fh * 4) * (VT * 3) + vl * 3;
+                float vx[4], vy[4], vz[4];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const uint32_t* q = t + f * 12;
+                    const float x = vx[f], y = vy[f], z = vz[f];
+                    p[f * (VT * 3)] = __uint_as_float(q[0]) * x + __uint_as_float(q[1]) * y + __uint_as_float(q[2]) * z + __uint_as_float(q[3]);
+                    p[f * (VT * 3) + 1] = __uint_as_float(q[4]) * x + __uint_as_float(q[5]) * y + __uint_as_float(q[6]) * z + __uint_as_float(q[7]);
+                    p[f * (VT * 3) + 2] = __uint_as_float(q[8]) * x + __uint_as_float(q[9]) * y + __uint_as_float(q[10]) * z + __uint_as_float(q[11]);
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory");         // all 8 frames of the tile are in smem
+            if (HAS_JX) {
+                // partial dot product of the regressor row with this tile's skinned vertices:
+                // thread = (frame, 32-way split of the 128 vertices), then a warp shuffle reduction
+                const int f = warp, part = tid & 31;
+                float a = 0.f, bb = 0.f, c = 0.f;
+                if (f < nf) {
+                    const float* row = sV + f * (VT * 3);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                bb += __shfl_xor_sync(0xffffffffu, bb, o);
-                c += __shfl_xor_sync(0xffffffffu, c, o);
+                    for (int i = 0; i < VT / 32; ++i) {
+                        const int v = part + 32 * i;
+                        const float w = sJx[v];
+                        a = fmaf(w, row[v * 3], a); bb = fmaf(w, row[v * 3 + 1], bb); c = fmaf(w, row[v * 3 + 2], c);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        a += __shfl_xor_sync(0xffffffffu, a, o);
+                        bb += __shfl_xor_sync(0xffffffffu, bb, o);
+                        c += __shfl_xor_sync(0xffffffffu, c, o);
+                    }
+                    if (part == 0) {
+                        float* o = jx_partial + ((int64_t)tile * F + f0 + f) * 3;
+                        o[0] = a; o[1] = bb; o[2] = c;
+                    }
+                }
             }
-            if (part == 0 && f < nf) {
-                float* o = jx_partial + ((int64_t)tile * F + f0 + f) * 3;
-                o[0] = a; o[1] = bb; o[2] = c;
+            // coalesced stores: warp f writes frame f: nv*3 contiguous floats, 8-byte aligned (V even, v0*12 % 8 == 0)
+            {
+                const int f = warp, n2 = (nv * 3) >> 1, l = tid & 31;
+                if (f < nf) {
+                    float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
+                    const float2* src = reinterpret_cast<const float2*>(sV + f * (VT * 3));
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+                        if (l + 32 * i < n2) dst[l + 32 * i] = src[l + 32 * i];
+                }
             }
-        }
-        // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 multiple of 8)
-        const int n2 = (nv * 3) >> 1;
-#pragma unroll 2
-        for (int f = 0; f < nf; ++f) {
-            float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
-            const float2* src = reinterpret_cast<const float2*>(sV + f * (VT * 3));
-            if (tid < n2) dst[tid] = src[tid];
-            if (tid + VT < n2) dst[tid + VT] = src[tid + VT];
-        }
-        if (g + 2 < ng) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to this stage precede its TMA refill
-            __syncthreads();
-            if (tid == 0) issue_loads(g + 2, false);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic accesses precede the stage's TMA refill
+            mbar_arrive(EMPTY(s));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS2) : "memory");
+    if (warp == 9) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS3) : "memory");
     }
 }
 
@@ -299,16 +347,25 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
     GAIT_REQUIRE(aligned16(Aop) && aligned16(Wpack), "smpl_lbs_tc: operand blobs must be 16-byte aligned");
     GAIT_REQUIRE(F < (1ll << 31) && V < (1ll << 31) && ceil_div(F, lbs::FT) < 65536, "smpl_lbs_tc: size too large");
     static bool attr = false;
+    static int n_sms = 0;
     if (!attr) {
-        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM2));
-        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM2));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
+        int dev = 0;
+        GAIT_CUDA(cudaGetDevice(&dev));
+        GAIT_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
         attr = true;
     }
-    dim3 grid((unsigned)tiles, (unsigned)ceil_div(ceil_div(F, lbs::FT), lbs::GPC));
+    const int64_t groups = ceil_div(F, lbs::FT);
+    const int64_t n_items = tiles * groups;
+    GAIT_REQUIRE(n_items < (1ll << 31), "smpl_lbs_tc: too many work items");
+    const unsigned grid = (unsigned)std::min<int64_t>(n_items, n_sms);          // persistent: one CTA per SM
     if (jx)
-        lbs::smpl_lbs_tc_kernel<true><<<grid, lbs::VT, lbs::SMEM2, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V);
+        lbs::smpl_lbs_tc_kernel<true><<<grid, lbs::THREADS3, lbs::SMEM3, as_stream(stream)>>>(
+            v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V, (int)groups, (int)n_items);
     else
-        lbs::smpl_lbs_tc_kernel<false><<<grid, lbs::VT, lbs::SMEM2, as_stream(stream)>>>(v_posed, ldv, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V);
+        lbs::smpl_lbs_tc_kernel<false><<<grid, lbs::THREADS3, lbs::SMEM3, as_stream(stream)>>>(
+            v_posed, ldv, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V, (int)groups, (int)n_items);
     return check_launch("smpl_lbs_tc");
 }
 

@@ -14,7 +14,9 @@
 //                                (round-to-nearest) into FP32 registers; two TMEM buffers alternate.
 //                                Final: +bias +Cin -> coalesced global stores
 //
-// with mbarrier full/converted/empty rings (3 stages) and a TMEM-full barrier.  Dropped term:
+// with mbarrier full/converted/empty rings (3 stages) and accumulator full/empty rings (4 TMEM buffers);
+// CTAs are persistent (one per SM) and walk (tile, k-split) work items, so the stores of one item overlap the
+// loads and MMAs of the next.  Dropped term:
 // P_lo.Q_lo ~ 2^-22 relative.  The same kernel serves C = A.W^T (P = A) and the transposed
 // form (P = W, Q = A) that keeps 128 TMEM lanes busy when A has few rows (GRU recurrence,
 // S = 64); split-K over blockIdx.z writes partial sums that the consumer adds.
@@ -39,10 +41,10 @@ struct Cfg {
     static constexpr int P_TILE = BM * BK * 4;
     static constexpr int Q_TILE = BN * BK * 4;
     static constexpr int STAGE = 2 * P_TILE + 2 * Q_TILE;     // [P hi][P lo][Q hi][Q lo]
-    static constexpr int STAGING = 4 * 32 * 33 * 4;
-    static constexpr int BAR_BYTES = 128;
+    static constexpr int STAGING = 4 * 32 * 36 * 4;
+    static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM = STAGES * STAGE + STAGING + BAR_BYTES + 1024;   // +1024 alignment slack
-    static constexpr int TMEM_COLS = 2 * BN;                  // two accumulator buffers
+    static constexpr int TMEM_COLS = 4 * BN;                  // ring of four accumulator buffers
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,29 +108,30 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
 }
 
 // barrier slots (8 B each)
-enum : int { B_FULL = 0, B_CONV = 3, B_EMPTY = 6, B_ACC_FULL = 9, B_ACC_EMPTY = 11 };
+constexpr int NBUF = 4;                    // TMEM accumulator buffers (ring)
+enum : int { B_FULL = 0, B_CONV = 3, B_EMPTY = 6, B_ACC_FULL = 9, B_ACC_EMPTY = 9 + NBUF };
 
+// Persistent kernel: each CTA walks work items (p tile, q tile, k split) item = blockIdx.x + i*gridDim.x.
+// The smem stage ring and the TMEM accumulator ring run continuously across items, so the TMA / convert /
+// MMA roles work on item i+1 while the promotion warps are still storing item i.
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
-                   int P_rows, int Q_rows, int K, int transposed, int kb_per_split, int64_t split_stride, int mode) {
+                   int P_rows, int Q_rows, int K, int transposed, int kb_per_split, int64_t split_stride,
+                   int tiles_q, int splits, int n_items, int mode) {
     using cfg = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + STAGES * cfg::STAGE + cfg::STAGING;
     auto BAR = [&](int i) { return bars + 8u * i; };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * cfg::STAGE + cfg::STAGING + 112);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * cfg::STAGE + cfg::STAGING + 240);
     float* staging = reinterpret_cast<float*>(gbase + STAGES * cfg::STAGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p0 = blockIdx.x * BM, q0 = blockIdx.y * BN;
     const int nkb_total = (K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * kb_per_split;
-    const int nkb = min(kb_per_split, nkb_total - kb0);
     const int drain_kb = (mode == 2) ? (1 << 30) : DRAIN_KB;          // mode 2 (debug): never promote
-    const int nchunks = (nkb + drain_kb - 1) / drain_kb;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -136,7 +139,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             mbar_init(BAR(B_CONV + s), NCONV);
             mbar_init(BAR(B_EMPTY + s), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(BAR(B_ACC_FULL + b), 1);
             mbar_init(BAR(B_ACC_EMPTY + b), NDRAIN);
         }
@@ -151,137 +154,178 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == 0) {
-        // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
-                const uint32_t st = base + s * cfg::STAGE;
-                mbar_arrive_expect_tx(BAR(B_FULL + s), cfg::P_TILE + cfg::Q_TILE);
-                tma_load_2d(st, &tmP, (kb0 + kb) * BK, p0, BAR(B_FULL + s));
-                tma_load_2d(st + 2 * cfg::P_TILE, &tmQ, (kb0 + kb) * BK, q0, BAR(B_FULL + s));
+    int it = 0;        // k-blocks processed so far by this CTA (position in the stage ring)
+    int ch = 0;        // accumulator chunks processed so far (position in the TMEM ring)
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int z = item % splits;
+        const int qt = (item / splits) % tiles_q;
+        const int pt = item / (splits * tiles_q);
+        const int p0 = pt * BM, q0 = qt * BN;
+        const int kb0 = z * kb_per_split;
+        const int nkb = min(kb_per_split, nkb_total - kb0);
+        const int nchunks = (nkb + drain_kb - 1) / drain_kb;
+
+        if (warp == 0) {
+            // ------------------------------------------------------------ TMA producer
+            if (lane == 0) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int s = (it + kb) % STAGES;
+                    const uint32_t ph = ((it + kb) / STAGES) & 1;
+                    mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+                    const uint32_t st = base + s * cfg::STAGE;
+                    mbar_arrive_expect_tx(BAR(B_FULL + s), cfg::P_TILE + cfg::Q_TILE);
+                    tma_load_2d(st, &tmP, (kb0 + kb) * BK, p0, BAR(B_FULL + s));
+                    tma_load_2d(st + 2 * cfg::P_TILE, &tmQ, (kb0 + kb) * BK, q0, BAR(B_FULL + s));
+                }
             }
-        }
-    } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                const int chunk = kb / drain_kb, buf = chunk & 1;
-                const bool chunk_start = (kb % drain_kb) == 0;
-                if (chunk_start && chunk >= 2) mbar_wait(BAR(B_ACC_EMPTY + buf), ((chunk >> 1) - 1) & 1);
-                mbar_wait(BAR(B_CONV + s), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_d + (uint32_t)(buf * BN);
-                const uint32_t st = base + s * cfg::STAGE;
-                const uint64_t p_hi = make_sdesc(st), p_lo = make_sdesc(st + cfg::P_TILE);
-                const uint64_t q_hi = make_sdesc(st + 2 * cfg::P_TILE), q_lo = make_sdesc(st + 2 * cfg::P_TILE + cfg::Q_TILE);
+        } else if (warp == 1) {
+            // ------------------------------------------------------------ MMA issuer
+            if (lane == 0) {
+                constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int s = (it + kb) % STAGES;
+                    const uint32_t ph = ((it + kb) / STAGES) & 1;
+                    const int cg = ch + kb / drain_kb, buf = cg % NBUF, use = cg / NBUF;
+                    const bool chunk_start = (kb % drain_kb) == 0;
+                    if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
+                    mbar_wait(BAR(B_CONV + s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t acc = tmem_d + (uint32_t)(buf * BN);
+                    const uint32_t st = base + s * cfg::STAGE;
+                    const uint64_t p_hi = make_sdesc(st), p_lo = make_sdesc(st + cfg::P_TILE);
+                    const uint64_t q_hi = make_sdesc(st + 2 * cfg::P_TILE), q_lo = make_sdesc(st + 2 * cfg::P_TILE + cfg::Q_TILE);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);       // 8 floats = 32 bytes along K inside the swizzle span
-                    const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
-                    if (mode == 1) {                                        // debug: plain TF32
-                        umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, first);
-                    } else {
-                        umma_tf32(acc, p_lo + adv, q_hi + adv, idesc, first);
-                        umma_tf32(acc, p_hi + adv, q_lo + adv, idesc, 1u);
-                        umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, 1u);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 floats = 32 bytes along K inside the swizzle span
+                        const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
+                        if (mode == 1) {                                    // debug: plain TF32
+                            umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, first);
+                        } else {
+                            umma_tf32(acc, p_lo + adv, q_hi + adv, idesc, first);
+                            umma_tf32(acc, p_hi + adv, q_lo + adv, idesc, 1u);
+                            umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, 1u);
+                        }
                     }
+                    umma_commit(BAR(B_EMPTY + s));                          // frees the stage when the MMAs retire
+                    if ((kb % drain_kb) == drain_kb - 1 || kb == nkb - 1) umma_commit(BAR(B_ACC_FULL + buf));
                 }
-                umma_commit(BAR(B_EMPTY + s));                              // frees the stage when the MMAs retire
-                if ((kb % drain_kb) == drain_kb - 1 || kb == nkb - 1) umma_commit(BAR(B_ACC_FULL + buf));
             }
-        }
-    } else if (warp < 6) {
-        // ---------------------------------------------------------------- converters: x -> (tf32 hi, lo)
-        const int ct = threadIdx.x - 64;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(BAR(B_FULL + s), ph);
-            uint8_t* st = gbase + s * cfg::STAGE;
-            auto convert = [&](uint8_t* hi, uint8_t* lo, int chunks) {
+        } else if (warp < 6) {
+            // ------------------------------------------------------------ converters: x -> (tf32 hi, lo)
+            const int ct = threadIdx.x - 64;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = (it + kb) % STAGES;
+                const uint32_t ph = ((it + kb) / STAGES) & 1;
+                mbar_wait(BAR(B_FULL + s), ph);
+                uint8_t* st = gbase + s * cfg::STAGE;
+                auto convert = [&](uint8_t* hi, uint8_t* lo, int chunks) {
 #pragma unroll 4
-                for (int c = ct; c < chunks; c += NCONV) {
-                    float4 v = *reinterpret_cast<float4*>(hi + c * 16);
-                    float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
-                    float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-                    *reinterpret_cast<float4*>(hi + c * 16) = h;
-                    *reinterpret_cast<float4*>(lo + c * 16) = l;
-                }
-            };
-            convert(st, st + cfg::P_TILE, cfg::P_TILE / 16);
-            convert(st + 2 * cfg::P_TILE, st + 2 * cfg::P_TILE + cfg::Q_TILE, cfg::Q_TILE / 16);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(BAR(B_CONV + s));
-        }
-    } else {
-        // ---------------------------------------------------------------- promotion + epilogue
-        // The tensor core adds into its FP32 accumulator with truncation, so error grows linearly
-        // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every DRAIN_KB
-        // k-blocks the TMEM partial sum is therefore added (round-to-nearest) into FP32 registers.
-        const int quad = warp & 3;                                  // this warp owns TMEM lanes 32*quad .. +31
-        float accr[BN];
+                    for (int c = ct; c < chunks; c += NCONV) {
+                        float4 v = *reinterpret_cast<float4*>(hi + c * 16);
+                        float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+                        float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                        *reinterpret_cast<float4*>(hi + c * 16) = h;
+                        *reinterpret_cast<float4*>(lo + c * 16) = l;
+                    }
+                };
+                convert(st, st + cfg::P_TILE, cfg::P_TILE / 16);
+                convert(st + 2 * cfg::P_TILE, st + 2 * cfg::P_TILE + cfg::Q_TILE, cfg::Q_TILE / 16);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(BAR(B_CONV + s));
+            }
+        } else {
+            // ------------------------------------------------------------ promotion + epilogue
+            // The tensor core adds into its FP32 accumulator with truncation, so error grows linearly
+            // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every DRAIN_KB
+            // k-blocks the TMEM partial sum is therefore added (round-to-nearest) into FP32 registers.
+            const int quad = warp & 3;                              // this warp owns TMEM lanes 32*quad .. +31
+            float accr[BN];
 #pragma unroll
-        for (int j = 0; j < BN; ++j) accr[j] = 0.f;
-        for (int chunk = 0; chunk < nchunks; ++chunk) {
-            const int buf = chunk & 1;
-            mbar_wait(BAR(B_ACC_FULL + buf), (chunk >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int j = 0; j < BN; ++j) accr[j] = 0.f;
+            for (int chunk = 0; chunk < nchunks; ++chunk) {
+                const int cg = ch + chunk, buf = cg % NBUF, use = cg / NBUF;
+                mbar_wait(BAR(B_ACC_FULL + buf), use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) accr[c * 32 + j] += __uint_as_float(r[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(BAR(B_ACC_EMPTY + buf));
+            }
+            const int prow = p0 + quad * 32 + lane;
+            const bool first_split = z == 0;
+            float* Cz = C + z * split_stride;
+            float* stg = staging + quad * 32 * 36;
+            const bool vec = !transposed && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15u) == 0) &&
+                             (!(Cin && first_split) || (((ldcin & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cin) & 15u) == 0))) &&
+                             (!(bias && first_split) || ((reinterpret_cast<uintptr_t>(bias) & 15u) == 0));
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+                if (transposed) {
+                    // D row = output column: lanes run along the contiguous output dimension
+                    if (prow < P_rows) {
+                        const float bv = (bias && first_split) ? bias[prow] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) accr[c * 32 + j] += __uint_as_float(r[j]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(BAR(B_ACC_EMPTY + buf));
-        }
-        const int prow = p0 + quad * 32 + lane;
-        const bool first_split = blockIdx.z == 0;
-        float* Cz = C + blockIdx.z * split_stride;
-        float* stg = staging + quad * 32 * 33;
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-            if (transposed) {
-                // D row = output column: lanes run along the contiguous output dimension
-                if (prow < P_rows) {
-                    const float bv = (bias && first_split) ? bias[prow] : 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int qrow = q0 + c * 32 + j;
-                        if (qrow < Q_rows) {
-                            float o = accr[c * 32 + j] + bv;
-                            if (Cin && first_split) o += Cin[(int64_t)qrow * ldcin + prow];
-                            Cz[(int64_t)qrow * ldc + prow] = o;
+                        for (int j = 0; j < 32; ++j) {
+                            const int qrow = q0 + c * 32 + j;
+                            if (qrow < Q_rows) {
+                                float o = accr[c * 32 + j] + bv;
+                                if (Cin && first_split) o += Cin[(int64_t)qrow * ldcin + prow];
+                                Cz[(int64_t)qrow * ldc + prow] = o;
+                            }
                         }
                     }
-                }
-            } else {
+                } else {
+                    // transpose through smem (row stride 36 floats: conflict-free 16-byte accesses both ways)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = accr[c * 32 + j];
-                __syncwarp();
-                const int col = q0 + c * 32 + lane;
-                if (col < Q_rows) {
-                    const float bv = (bias && first_split) ? bias[col] : 0.f;
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(stg + lane * 36 + j) =
+                            make_float4(accr[c * 32 + j], accr[c * 32 + j + 1], accr[c * 32 + j + 2], accr[c * 32 + j + 3]);
+                    __syncwarp();
+                    const int colbase = q0 + c * 32;
+                    if (vec && colbase + 32 <= Q_rows) {
+                        const int col = colbase + (lane & 7) * 4;
+                        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias && first_split) bv = *reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+                        for (int r4 = 0; r4 < 32; r4 += 4) {
+                            const int rr = r4 + (lane >> 3);
+                            const int row = p0 + quad * 32 + rr;
+                            if (row < P_rows) {
+                                float4 o = *reinterpret_cast<const float4*>(stg + rr * 36 + (lane & 7) * 4);
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                                if (Cin && first_split) {
+                                    const float4 cv = *reinterpret_cast<const float4*>(Cin + (int64_t)row * ldcin + col);
+                                    o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
+                                }
+                                *reinterpret_cast<float4*>(Cz + (int64_t)row * ldc + col) = o;
+                            }
+                        }
+                    } else {
+                        const int col = colbase + lane;
+                        if (col < Q_rows) {
+                            const float bv = (bias && first_split) ? bias[col] : 0.f;
 #pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = p0 + quad * 32 + rr;
-                        if (row < P_rows) {
-                            float o = stg[rr * 33 + lane] + bv;
-                            if (Cin && first_split) o += Cin[(int64_t)row * ldcin + col];
-                            Cz[(int64_t)row * ldc + col] = o;
+                            for (int rr = 0; rr < 32; ++rr) {
+                                const int row = p0 + quad * 32 + rr;
+                                if (row < P_rows) {
+                                    float o = stg[rr * 36 + lane] + bv;
+                                    if (Cin && first_split) o += Cin[(int64_t)row * ldcin + col];
+                                    Cz[(int64_t)row * ldc + col] = o;
+                                }
+                            }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
+        it += nkb;
+        ch += nchunks;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -347,14 +391,25 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const float* b
         set_error("linear(tc): K=%d cannot be cut into %d non-empty splits", K, splits);
         return GAIT_ERR_INVALID;
     }
-    dim3 grid((unsigned)ceil_div(P_rows, BM), (unsigned)ceil_div(Q_rows, BN), (unsigned)splits);
+    const int tiles_p = (int)ceil_div(P_rows, BM), tiles_q = (int)ceil_div(Q_rows, BN);
+    const int n_items = tiles_p * tiles_q * splits;
+    static int n_sms = 0;
+    if (n_sms == 0) {
+        int dev = 0;
+        GAIT_CUDA(cudaGetDevice(&dev));
+        GAIT_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // persistent CTAs, one per SM; balance the number of items per CTA
+    const int per_cta = (int)ceil_div(n_items, n_sms);
+    dim3 grid((unsigned)ceil_div(n_items, per_cta));
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("GAITB200_TC_MODE");
         mode = e ? atoi(e) : 0;
     }
     gemm_tf32x3_kernel<BN><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
-                                                                transposed, kb_per_split, split_stride, mode);
+                                                                transposed, kb_per_split, split_stride, tiles_q, splits,
+                                                                n_items, mode);
     return check_launch("linear(tf32x3 tcgen05)");
 }
 

@@ -40,9 +40,10 @@ class GaitHead(nn.Module):
         self.eval()
         self._plan = None
         self._graph = None
+        self._slots, self._graphs = [], []
 
     # ------------------------------------------------------------------ buffers for one (S,T)
-    def plan(self, S: int, T: int):
+    def _make_plan(self, S: int, T: int):
         dev = self.regressor.fc1.weight.device
         if dev.type != "cuda":
             raise L.GaitLibraryError("GaitHead is on %s; move it to a CUDA device (no CPU path)" % dev)
@@ -65,9 +66,16 @@ class GaitHead(nn.Module):
             "joints": e(F, 29, 3), "kp2d": e(F, 29, 2), "kinect": e(F, 25, 3), "theta": e(F, 85),
             "gather": torch.tensor(SPIN2_TO_KINECTV2, dtype=torch.int32, device=dev),
         }
-        self._plan = p
-        self._graph = None
         return p
+
+    def plan(self, S: int, T: int, slots: int = 1):
+        """Allocate `slots` independent buffer sets for (S,T) (slot 0 is the default one; a second
+        slot lets the D2H copy of one batch overlap the kernels of the next, see run_host_batches)."""
+        self._slots = [self._make_plan(S, T) for _ in range(max(1, slots))]
+        self._graphs = [None] * len(self._slots)
+        self._plan = self._slots[0]
+        self._graph = None
+        return self._plan
 
     def _stages(self, p):
         """The step as an ordered list of (name, thunk); each thunk enqueues one stage on the
@@ -138,25 +146,69 @@ class GaitHead(nn.Module):
             res[name] = {"ms": tot / iters, "launches": (L.launch_count() - n0) // iters}
         return res
 
-    def capture(self, S: int, T: int):
-        """Plan buffers for (S,T) and capture one step into a CUDA graph."""
-        p = self.plan(S, T)
+    def capture(self, S: int, T: int, slots: int = 1):
+        """Plan buffers for (S,T) and capture one step per slot into a CUDA graph."""
+        self.plan(S, T, slots)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self._launch(p)                      # warm-up outside capture (lazy module loading)
+            self._launch(self._slots[0])         # warm-up outside capture (lazy module loading)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        n0 = L.launch_count()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._launch(p)
-        self.launches_per_step = L.launch_count() - n0
-        self._graph = g
-        return g
+        for i, p in enumerate(self._slots):
+            n0 = L.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(p)
+            self.launches_per_step = L.launch_count() - n0
+            self._graphs[i] = g
+        self._graph = self._graphs[0]
+        return self._graph
 
-    def outputs(self):
-        p = self._plan
+    @torch.no_grad()
+    def run_host_batches(self, inputs, outputs):
+        """End-to-end path for HOST data: for every batch, pinned features (S,T,2048) -> H2D -> one step ->
+        D2H of every output into the matching dict of pinned host tensors.  With two planned slots the
+        three phases of consecutive batches overlap on separate streams (copy-in, compute, copy-out);
+        returns after the last D2H has completed.  `outputs[i]` needs the keys of self.outputs()."""
+        if self._plan is None:
+            raise L.GaitLibraryError("call plan()/capture() first")
+        ns = len(self._slots)
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_io_streams"):
+            self._io_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        s_in, s_out = self._io_streams
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        ev_in = [None] * ns          # H2D of the slot's input finished
+        ev_cmp = [None] * ns         # the slot's kernels finished
+        ev_out = [None] * ns         # D2H of the slot's outputs finished
+        for i, (x_host, out_host) in enumerate(zip(inputs, outputs)):
+            k = i % ns
+            p = self._slots[k]
+            with torch.cuda.stream(s_in):
+                if ev_cmp[k] is not None:
+                    s_in.wait_event(ev_cmp[k])               # previous batch in this slot consumed its input
+                p["x"].copy_(x_host, non_blocking=True)
+                ev_in[k] = s_in.record_event()
+            cur.wait_event(ev_in[k])
+            if ev_out[k] is not None:
+                cur.wait_event(ev_out[k])                    # previous outputs of this slot are on the host
+            if self._graphs[k] is not None:
+                self._graphs[k].replay()
+            else:
+                self._launch(p)
+            ev_cmp[k] = cur.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[k])
+                for key, v in self.outputs(k).items():
+                    out_host[key].copy_(v, non_blocking=True)
+                ev_out[k] = s_out.record_event()
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+
+    def outputs(self, slot: int = 0):
+        p = self._slots[slot]
         S, T = p["S"], p["T"]
         v = lambda t: t.view(S, T, *t.shape[1:])
         out = {"theta": v(p["theta"]), "kp_2d": v(p["kp2d"]), "kp_3d": v(p["joints"]), "rotmat": v(p["rotmat"]),
