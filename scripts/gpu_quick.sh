@@ -15,3 +15,8 @@ if [ -n "$NCU" ]; then
       python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
   tail -2 $OUT/${TAG}_ncu.log | cut -c1-200
 fi
+if [ -n "${LAUNCHLIST:-}" ]; then
+  echo "== ncu launch list"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
+fi

@@ -25,6 +25,8 @@
 //   stores of group g.  86 KB smem + 256 TMEM columns per CTA: 2 CTAs per SM.
 #include <algorithm>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gait {
@@ -93,29 +95,33 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
 
 // Persistent, warp-specialised kernel: one CTA per SM walks a contiguous range of work items
 // (vertex tile, 8-frame group) in tile-major order.
-//   warp 8  (1 thread)  producer : TMA loads into a 4-stage ring (transform blob + 8 v_posed rows per item),
-//                                  weight blob reloaded when the range crosses into the next vertex tile
-//   warp 9  (1 thread)  MMA      : 9 tcgen05.mma per item into TMEM buffer = stage
-//   warps 0-7           compute  : warp w owns TMEM lanes 32*(w%4).. (= vertices) and frames 4*(w/4)..+3:
-//                                  tcgen05.ld T, apply to v_posed in smem, fused regressor-row partial,
-//                                  coalesced stores, then release the stage
-// Loads run up to 3 items ahead of the epilogue, which is what hides the TMA/HBM latency.
-constexpr int NS = 4;                                    // stages = TMEM accumulator buffers
+//   producer warp (1 thread) : TMA loads into a 4-stage ring (transform blob + 8 v_posed rows per item),
+//                              weight blob reloaded when the range crosses into the next vertex tile
+//   MMA warp (1 thread)      : 9 tcgen05.mma per item into TMEM buffer = stage
+//   NG consumer groups of 4 warps, items dealt round-robin: warp q of a group owns TMEM lanes 32q..
+//                              (= vertices): tcgen05.ld T for 8 frames, apply to v_posed in smem, fused
+//                              regressor-row partial, coalesced stores, then release the stage
+// Loads run up to 3 items ahead and two epilogues are in flight, which hides the TMA/HBM/TMEM latencies.
+constexpr int NS = 5;                                    // stages = TMEM accumulator buffers (5 x 96 = 480 columns)
+constexpr int NG = 3;                                    // consumer groups
 constexpr int STAGE = A_BLOB + FT * V_ROW;               // 30 720 B
 constexpr int OFF_STAGE = W_BLOB;
-constexpr int OFF_JX = OFF_STAGE + NS * STAGE;           // 128 floats of the fused regressor row
-constexpr int OFF_BAR = OFF_JX + VT * 4;
-constexpr int SMEM3 = OFF_BAR + 128;
+constexpr int OFF_JX = OFF_STAGE + NS * STAGE;           // NG x 128 floats of the fused regressor row
+constexpr int OFF_BAR = OFF_JX + NG * VT * 4;
+constexpr int SMEM3 = OFF_BAR + 192;
 constexpr int TMEM_COLS3 = 512;                          // NS x 96 columns -> 512 (power of two)
-constexpr int NCOMPUTE = 256;
+constexpr int NCOMPUTE = NG * 128;
 constexpr int THREADS3 = NCOMPUTE + 64;
 
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -124,33 +130,33 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 template <bool HAS_JX>
 __global__ void __launch_bounds__(THREADS3, 1)
-smpl_lbs_tc_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* __restrict__ Aop,
+smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restrict__ Aop,
                    const float* __restrict__ Wpack, const float* __restrict__ jx, float* __restrict__ verts,
                    float* __restrict__ jx_partial, int F, int V, int groups, int n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
-    float* sJx = reinterpret_cast<float*>(smem + OFF_JX);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto FULL = [&](int s) { return bar0 + 8u * s; };               // TMA landed (tx count)
-    auto MMAD = [&](int s) { return bar0 + 32u + 8u * s; };         // accumulator ready
-    auto EMPTY = [&](int s) { return bar0 + 64u + 8u * s; };        // compute warps done with the stage
-    const uint32_t WFULL = bar0 + 96u;                              // weight blob landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 112);
+    auto MMAD = [&](int s) { return bar0 + 8u * (NS + s); };        // accumulator ready
+    auto EMPTY = [&](int s) { return bar0 + 8u * (2 * NS + s); };   // consumer group done with the stage
+    const uint32_t WFULL = bar0 + 8u * (3 * NS);                    // weight blob landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (3 * NS + 1));
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // contiguous, balanced item range of this CTA; item = tile * groups + group
     const int item_lo = (int)(((int64_t)n_items * blockIdx.x) / gridDim.x);
     const int item_hi = (int)(((int64_t)n_items * (blockIdx.x + 1)) / gridDim.x);
+    const int tile_lo = item_lo / groups, g_lo = item_lo % groups;
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(FULL(s)) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(s)) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(s)), "r"(NCOMPUTE) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(s)), "r"(128) : "memory");
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WFULL) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == NCOMPUTE / 32 + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS3) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -159,44 +165,40 @@ smpl_lbs_tc_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == NCOMPUTE / 32) {
         // ---------------------------------------------------------------- producer
-        if (tid == NCOMPUTE) {
-            int cur_tile = -1, wuse = 0;
-            for (int item = item_lo; item < item_hi; ++item) {
-                const int n = item - item_lo, s = n % NS;
-                const int tile = item / groups, g = item % groups;
+        if (lane == 0) {
+            int cur_tile = -1, tile = tile_lo, g = g_lo;
+            for (int n = 0; n < item_hi - item_lo; ++n) {
+                const int s = n % NS;
                 if (n >= NS) mbar_wait(EMPTY(s), ((n / NS) - 1) & 1);
                 if (tile != cur_tile) {
                     // the previous tile's MMAs (which read the weight blob) must have retired: its last item is
-                    // item-1, whose stage is released only after its accumulator was consumed
-                    if (cur_tile >= 0) {
-                        const int pn = n - 1;
-                        mbar_wait(EMPTY(pn % NS), (pn / NS) & 1);
-                    }
+                    // n-1, whose stage is released only after its accumulator was consumed
+                    if (cur_tile >= 0) mbar_wait(EMPTY((n - 1) % NS), ((n - 1) / NS) & 1);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(WFULL), "r"((uint32_t)W_BLOB) : "memory");
                     bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, WFULL);
                     cur_tile = tile;
-                    ++wuse;
                 }
-                const int f0 = g * FT, nf = min(FT, F - f0);
                 const uint32_t st = smem_u32(smem + OFF_STAGE + s * STAGE);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)(A_BLOB + nf * V_ROW)) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)STAGE) : "memory");
                 bulk_g2s(st, Aop + (int64_t)g * (A_BLOB / 4), A_BLOB, FULL(s));
-                for (int f = 0; f < nf; ++f)
-                    bulk_g2s(st + A_BLOB + f * V_ROW, v_posed + (int64_t)(f0 + f) * ldv + (int64_t)tile * (VT * 3), V_ROW, FULL(s));
+                // 8 rows x 1536 B of v_posed as one 2D tensor copy (64-bit elements; rows past F read as zero)
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                    ::"r"(st + A_BLOB), "l"(reinterpret_cast<uint64_t>(&tmV)), "r"(tile * (VT * 3 / 2)), "r"(g * FT), "r"(FULL(s)) : "memory");
+                if (++g == groups) { g = 0; ++tile; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == NCOMPUTE / 32 + 1) {
         // ---------------------------------------------------------------- MMA issuer
-        if (tid == NCOMPUTE + 32) {
+        if (lane == 0) {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
             constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
             const uint32_t w_hi = smem_u32(smem), w_lo = w_hi + W_PART;
-            int cur_tile = -1, wuse = 0;
-            for (int item = item_lo; item < item_hi; ++item) {
-                const int n = item - item_lo, s = n % NS;
-                const int tile = item / groups;
+            int cur_tile = -1, wuse = 0, tile = tile_lo, g = g_lo;
+            for (int n = 0; n < item_hi - item_lo; ++n) {
+                const int s = n % NS;
                 if (tile != cur_tile) {
                     mbar_wait(WFULL, wuse & 1);
                     cur_tile = tile;
@@ -217,42 +219,45 @@ smpl_lbs_tc_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* 
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(s)) : "memory");
+                if (++g == groups) { g = 0; ++tile; }
             }
         }
     } else {
-        // ---------------------------------------------------------------- compute warps
-        const int quad = warp & 3, fh = warp >> 2;                 // TMEM lane quarter, frame half (frames 4*fh..+3)
-        const int vl = quad * 32 + (tid & 31);                     // vertex within the tile = TMEM lane
-        int cur_tile = -1;
-        for (int item = item_lo; item < item_hi; ++item) {
-            const int n = item - item_lo, s = n % NS;
+        // ---------------------------------------------------------------- consumer groups
+        const int grp = warp >> 2, quad = warp & 3;                // group, TMEM lane quarter
+        const int gt = tid & 127;                                  // thread within the group = vertex within the tile
+        float* sJx = reinterpret_cast<float*>(smem + OFF_JX) + grp * VT;
+        int cur_tile = -1, tile = tile_lo, g = g_lo + grp;
+        while (g >= groups) { g -= groups; ++tile; }
+        for (int n = grp; n < item_hi - item_lo; n += NG) {
+            const int s = n % NS;
             const uint32_t ph = (n / NS) & 1;
-            const int tile = item / groups, g = item % groups;
             const int v0 = tile * VT, nv = min(VT, V - v0);
             const int f0 = g * FT, nf = min(FT, F - f0);
             float* sV = reinterpret_cast<float*>(smem + OFF_STAGE + s * STAGE + A_BLOB);
             if (HAS_JX && tile != cur_tile) {
-                asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory");     // previous tile's partial pass finished
-                if (tid < VT) sJx[tid] = (tid < nv) ? jx[v0 + tid] : 0.f;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");    // previous tile's partial pass finished
+                sJx[gt] = (gt < nv) ? jx[v0 + gt] : 0.f;
                 cur_tile = tile;
             }
             mbar_wait(FULL(s), ph);                                // v_posed rows visible
             mbar_wait(MMAD(s), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {
-                // 4 frames x 12 accumulator columns of this vertex, and its 4 v_posed entries, fetched up front
-                uint32_t t[48];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * NCOL + fh * 48);
-                tmem_ld16_nowait(taddr, t);
-                tmem_ld16_nowait(taddr + 16, t + 16);
-                tmem_ld16_nowait(taddr + 32, t + 32);
-                float* p = sV + (fh * 4) * (VT * 3) + vl * 3;
-                float vx[4], vy[4], vz[4];
+                // all 96 accumulator columns of this vertex and its 8 v_posed entries are fetched up front
+                // (one TMEM round trip, one smem round trip), then 8 independent 3x4 applies
+                uint32_t t[NCOL];
+                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * NCOL);
+                tmem_ld32_nowait(taddr, t);
+                tmem_ld32_nowait(taddr + 32, t + 32);
+                tmem_ld32_nowait(taddr + 64, t + 64);
+                float vx[FT], vy[FT], vz[FT];
+                float* p = sV + gt * 3;
 #pragma unroll
-                for (int f = 0; f < 4; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
+                for (int f = 0; f < FT; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
+                for (int f = 0; f < FT; ++f) {
                     const uint32_t* q = t + f * 12;
                     const float x = vx[f], y = vy[f], z = vz[f];
                     p[f * (VT * 3)] = __uint_as_float(q[0]) * x + __uint_as_float(q[1]) * y + __uint_as_float(q[2]) * z + __uint_as_float(q[3]);
@@ -261,50 +266,50 @@ smpl_lbs_tc_kernel(const float* __restrict__ v_posed, int64_t ldv, const float* 
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory");         // all 8 frames of the tile are in smem
-            if (HAS_JX) {
-                // partial dot product of the regressor row with this tile's skinned vertices:
-                // thread = (frame, 32-way split of the 128 vertices), then a warp shuffle reduction
-                const int f = warp, part = tid & 31;
-                float a = 0.f, bb = 0.f, c = 0.f;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // the whole tile is in smem
+            const int n2 = (nv * 3) >> 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int f = quad + 4 * h;                        // warp q handles frames q and q+4
                 if (f < nf) {
                     const float* row = sV + f * (VT * 3);
+                    if (HAS_JX) {
+                        // partial dot product of the regressor row with this tile's skinned vertices
+                        float a = 0.f, bb = 0.f, c = 0.f;
 #pragma unroll
-                    for (int i = 0; i < VT / 32; ++i) {
-                        const int v = part + 32 * i;
-                        const float w = sJx[v];
-                        a = fmaf(w, row[v * 3], a); bb = fmaf(w, row[v * 3 + 1], bb); c = fmaf(w, row[v * 3 + 2], c);
-                    }
+                        for (int i = 0; i < VT / 32; ++i) {
+                            const int v = lane + 32 * i;
+                            const float w = sJx[v];
+                            a = fmaf(w, row[v * 3], a); bb = fmaf(w, row[v * 3 + 1], bb); c = fmaf(w, row[v * 3 + 2], c);
+                        }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        a += __shfl_xor_sync(0xffffffffu, a, o);
-                        bb += __shfl_xor_sync(0xffffffffu, bb, o);
-                        c += __shfl_xor_sync(0xffffffffu, c, o);
+                        for (int o = 16; o > 0; o >>= 1) {
+                            a += __shfl_xor_sync(0xffffffffu, a, o);
+                            bb += __shfl_xor_sync(0xffffffffu, bb, o);
+                            c += __shfl_xor_sync(0xffffffffu, c, o);
+                        }
+                        if (lane == 0) {
+                            float* o = jx_partial + ((int64_t)tile * F + f0 + f) * 3;
+                            o[0] = a; o[1] = bb; o[2] = c;
+                        }
                     }
-                    if (part == 0) {
-                        float* o = jx_partial + ((int64_t)tile * F + f0 + f) * 3;
-                        o[0] = a; o[1] = bb; o[2] = c;
-                    }
-                }
-            }
-            // coalesced stores: warp f writes frame f: nv*3 contiguous floats, 8-byte aligned (V even, v0*12 % 8 == 0)
-            {
-                const int f = warp, n2 = (nv * 3) >> 1, l = tid & 31;
-                if (f < nf) {
+                    // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 % 8 == 0)
                     float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
-                    const float2* src = reinterpret_cast<const float2*>(sV + f * (VT * 3));
+                    const float2* src = reinterpret_cast<const float2*>(row);
 #pragma unroll
                     for (int i = 0; i < 6; ++i)
-                        if (l + 32 * i < n2) dst[l + 32 * i] = src[l + 32 * i];
+                        if (lane + 32 * i < n2) dst[lane + 32 * i] = src[lane + 32 * i];
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic accesses precede the stage's TMA refill
             mbar_arrive(EMPTY(s));
+            g += NG;
+            while (g >= groups) { g -= groups; ++tile; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 9) {
+    if (warp == NCOMPUTE / 32 + 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS3) : "memory");
     }
 }
@@ -342,7 +347,7 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
     GAIT_REQUIRE((jx == nullptr) == (jx_partial == nullptr), "smpl_lbs_tc: jx and jx_partial go together");
     GAIT_REQUIRE((V & 1) == 0 && aligned8(verts), "smpl_lbs_tc: V must be even and verts 8-byte aligned");
     const int64_t tiles = ceil_div(V, lbs::VT);
-    GAIT_REQUIRE(ldv >= tiles * lbs::VT * 3 && (ldv & 3) == 0 && aligned16(v_posed),
+    GAIT_REQUIRE(ldv >= tiles * lbs::VT * 3 && (ldv & 3) == 0 && aligned16(v_posed) && F < (1ll << 31),
                  "smpl_lbs_tc: v_posed rows must be padded to 384*ceil(V/128) floats (ldv %% 4 == 0, 16-byte aligned)");
     GAIT_REQUIRE(aligned16(Aop) && aligned16(Wpack), "smpl_lbs_tc: operand blobs must be 16-byte aligned");
     GAIT_REQUIRE(F < (1ll << 31) && V < (1ll << 31) && ceil_div(F, lbs::FT) < 65536, "smpl_lbs_tc: size too large");
@@ -360,12 +365,15 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
     const int64_t n_items = tiles * groups;
     GAIT_REQUIRE(n_items < (1ll << 31), "smpl_lbs_tc: too many work items");
     const unsigned grid = (unsigned)std::min<int64_t>(n_items, n_sms);          // persistent: one CTA per SM
+    CUtensorMap tmV;
+    GAIT_TRY(make_tensor_map_2d(&tmV, 8, v_posed, (uint64_t)(tiles * lbs::VT * 3 / 2), (uint64_t)F, (uint64_t)ldv * sizeof(float),
+                                lbs::VT * 3 / 2, lbs::FT, false));
     if (jx)
         lbs::smpl_lbs_tc_kernel<true><<<grid, lbs::THREADS3, lbs::SMEM3, as_stream(stream)>>>(
-            v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V, (int)groups, (int)n_items);
+            tmV, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V, (int)groups, (int)n_items);
     else
         lbs::smpl_lbs_tc_kernel<false><<<grid, lbs::THREADS3, lbs::SMEM3, as_stream(stream)>>>(
-            v_posed, ldv, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V, (int)groups, (int)n_items);
+            tmV, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V, (int)groups, (int)n_items);
     return check_launch("smpl_lbs_tc");
 }
 
