@@ -93,6 +93,10 @@ int gait_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const 
                 const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                 gait_stream_t stream);
 
+/* Debug hook: device buffer of 64*4 uint64 that receives per-k-block pipeline timestamps (stage free, data
+ * landed, converted, MMAs issued) of CTA 0 of subsequent tensor-core GEMM launches; NULL disables. */
+int gait_debug_linear_trace(unsigned long long* device_buffer);
+
 /* ---- GRU: torch.nn.GRU as used by TemporalEncoder / gait_feat_encoder.py:51-57,88 --------- */
 size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H);
 /* One layer, one direction.  x (S,T,I) with frame stride ldx; weights in torch layout

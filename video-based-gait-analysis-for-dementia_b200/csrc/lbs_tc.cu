@@ -124,6 +124,12 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
+// one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -166,48 +172,50 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == NCOMPUTE / 32) {
-        // ---------------------------------------------------------------- producer
-        if (lane == 0) {
-            int cur_tile = -1, tile = tile_lo, g = g_lo;
-            for (int n = 0; n < item_hi - item_lo; ++n) {
-                const int s = n % NS;
-                if (n >= NS) mbar_wait(EMPTY(s), ((n / NS) - 1) & 1);
-                if (tile != cur_tile) {
-                    // the previous tile's MMAs (which read the weight blob) must have retired: its last item is
-                    // n-1, whose stage is released only after its accumulator was consumed
-                    if (cur_tile >= 0) mbar_wait(EMPTY((n - 1) % NS), ((n - 1) / NS) & 1);
+        // ---------------------------------------------------------------- producer (warp-uniform loop, one lane issues)
+        int cur_tile = -1, tile = tile_lo, g = g_lo;
+        for (int n = 0; n < item_hi - item_lo; ++n) {
+            const int s = n % NS;
+            if (n >= NS) mbar_wait(EMPTY(s), ((n / NS) - 1) & 1);
+            const bool new_tile = tile != cur_tile;
+            // the previous tile's MMAs (which read the weight blob) must have retired: its last item is
+            // n-1, whose stage is released only after its accumulator was consumed
+            if (new_tile && cur_tile >= 0) mbar_wait(EMPTY((n - 1) % NS), ((n - 1) / NS) & 1);
+            const uint32_t st = smem_u32(smem + OFF_STAGE + s * STAGE);
+            if (elect_one()) {
+                if (new_tile) {
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(WFULL), "r"((uint32_t)W_BLOB) : "memory");
                     bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, WFULL);
-                    cur_tile = tile;
                 }
-                const uint32_t st = smem_u32(smem + OFF_STAGE + s * STAGE);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)STAGE) : "memory");
                 bulk_g2s(st, Aop + (int64_t)g * (A_BLOB / 4), A_BLOB, FULL(s));
                 // 8 rows x 1536 B of v_posed as one 2D tensor copy (64-bit elements; rows past F read as zero)
                 asm volatile(
                     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                     ::"r"(st + A_BLOB), "l"(reinterpret_cast<uint64_t>(&tmV)), "r"(tile * (VT * 3 / 2)), "r"(g * FT), "r"(FULL(s)) : "memory");
-                if (++g == groups) { g = 0; ++tile; }
             }
+            __syncwarp();
+            cur_tile = tile;
+            if (++g == groups) { g = 0; ++tile; }
         }
     } else if (warp == NCOMPUTE / 32 + 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
-            constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
-            const uint32_t w_hi = smem_u32(smem), w_lo = w_hi + W_PART;
-            int cur_tile = -1, wuse = 0, tile = tile_lo, g = g_lo;
-            for (int n = 0; n < item_hi - item_lo; ++n) {
-                const int s = n % NS;
-                if (tile != cur_tile) {
-                    mbar_wait(WFULL, wuse & 1);
-                    cur_tile = tile;
-                    ++wuse;
-                }
-                mbar_wait(FULL(s), (n / NS) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(smem + OFF_STAGE + s * STAGE), a_lo = a_hi + A_PART;
-                const uint32_t acc = tmem_d + (uint32_t)(s * NCOL);
+        // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
+        constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
+        const uint32_t w_hi = smem_u32(smem), w_lo = w_hi + W_PART;
+        int cur_tile = -1, wuse = 0, tile = tile_lo, g = g_lo;
+        for (int n = 0; n < item_hi - item_lo; ++n) {
+            const int s = n % NS;
+            if (tile != cur_tile) {
+                mbar_wait(WFULL, wuse & 1);
+                cur_tile = tile;
+                ++wuse;
+            }
+            mbar_wait(FULL(s), (n / NS) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(smem + OFF_STAGE + s * STAGE), a_lo = a_hi + A_PART;
+            const uint32_t acc = tmem_d + (uint32_t)(s * NCOL);
+            if (elect_one()) {
                 // D[128 x 96] = W(128 x 24) . Aop(96 x 24)^T, split-TF32: small cross terms first
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -219,8 +227,9 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(s)) : "memory");
-                if (++g == groups) { g = 0; ++tile; }
             }
+            __syncwarp();
+            if (++g == groups) { g = 0; ++tile; }
         }
     } else {
         // ---------------------------------------------------------------- consumer groups

@@ -203,3 +203,11 @@ extern "C" int gait_linear(const float* A, int64_t lda, const float* W, int64_t 
                            int64_t K, gait_stream_t stream) {
     return gait::linear_launch(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, gait::as_stream(stream));
 }
+
+namespace gait { void linear_tc_set_trace(unsigned long long* p); }
+// Debug hook (not part of the reference-facing surface): device buffer of 64*4 uint64 receiving pipeline
+// timestamps of CTA 0 of the next tensor-core GEMM launches; NULL disables.
+extern "C" int gait_debug_linear_trace(unsigned long long* device_buffer) {
+    gait::linear_tc_set_trace(device_buffer);
+    return GAIT_OK;
+}

@@ -30,7 +30,7 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 4;
 constexpr int DRAIN_KB = 2;               // k-blocks accumulated in TMEM between promotions to FP32 registers
 constexpr int THREADS = 320;              // warp0 TMA, warp1 MMA/TMEM, warps 2-5 convert, warps 6-9 promote + epilogue
 constexpr int NCONV = 128;
@@ -41,6 +41,7 @@ struct Cfg {
     static constexpr int P_TILE = BM * BK * 4;
     static constexpr int Q_TILE = BN * BK * 4;
     static constexpr int STAGE = 2 * P_TILE + 2 * Q_TILE;     // [P hi][P lo][Q hi][Q lo]
+    static constexpr int STAGES = (BN <= 64) ? 4 : 3;         // 4 x 48 KB or 3 x 64 KB
     static constexpr int STAGING = 4 * 32 * 36 * 4;
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM = STAGES * STAGE + STAGING + BAR_BYTES + 1024;   // +1024 alignment slack
@@ -95,6 +96,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// round-to-nearest TF32 (10 explicit mantissa bits) with integer ops; the remainder x - hi is exact in FP32
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -109,7 +118,7 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
 
 // barrier slots (8 B each)
 constexpr int NBUF = 4;                    // TMEM accumulator buffers (ring)
-enum : int { B_FULL = 0, B_CONV = 3, B_EMPTY = 6, B_ACC_FULL = 9, B_ACC_EMPTY = 9 + NBUF };
+enum : int { B_FULL = 0, B_CONV = MAX_STAGES, B_EMPTY = 2 * MAX_STAGES, B_ACC_FULL = 3 * MAX_STAGES, B_ACC_EMPTY = 3 * MAX_STAGES + NBUF };
 
 // Persistent kernel: each CTA walks work items (p tile, q tile, k split) item = blockIdx.x + i*gridDim.x.
 // The smem stage ring and the TMEM accumulator ring run continuously across items, so the TMA / convert /
@@ -119,8 +128,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
                    int P_rows, int Q_rows, int K, int transposed, int kb_per_split, int64_t split_stride,
-                   int tiles_q, int splits, int n_items, int mode) {
+                   int tiles_q, int splits, int n_items, int mode, unsigned long long* trace) {
     using cfg = Cfg<BN>;
+    constexpr int STAGES = cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -167,33 +177,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
         if (warp == 0) {
             // ------------------------------------------------------------ TMA producer
-            if (lane == 0) {
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const int s = (it + kb) % STAGES;
-                    const uint32_t ph = ((it + kb) / STAGES) & 1;
-                    mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
-                    const uint32_t st = base + s * cfg::STAGE;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = (it + kb) % STAGES;
+                const uint32_t ph = ((it + kb) / STAGES) & 1;
+                mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+                const uint32_t st = base + s * cfg::STAGE;
+                if (elect_one()) {
+                    if (trace && blockIdx.x == 0 && it + kb < 64) trace[(it + kb) * 4 + 0] = clock64();
                     mbar_arrive_expect_tx(BAR(B_FULL + s), cfg::P_TILE + cfg::Q_TILE);
                     tma_load_2d(st, &tmP, (kb0 + kb) * BK, p0, BAR(B_FULL + s));
                     tma_load_2d(st + 2 * cfg::P_TILE, &tmQ, (kb0 + kb) * BK, q0, BAR(B_FULL + s));
                 }
+                __syncwarp();
             }
         } else if (warp == 1) {
             // ------------------------------------------------------------ MMA issuer
-            if (lane == 0) {
-                constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-                for (int kb = 0; kb < nkb; ++kb) {
-                    const int s = (it + kb) % STAGES;
-                    const uint32_t ph = ((it + kb) / STAGES) & 1;
-                    const int cg = ch + kb / drain_kb, buf = cg % NBUF, use = cg / NBUF;
-                    const bool chunk_start = (kb % drain_kb) == 0;
-                    if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
-                    mbar_wait(BAR(B_CONV + s), ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t acc = tmem_d + (uint32_t)(buf * BN);
-                    const uint32_t st = base + s * cfg::STAGE;
-                    const uint64_t p_hi = make_sdesc(st), p_lo = make_sdesc(st + cfg::P_TILE);
-                    const uint64_t q_hi = make_sdesc(st + 2 * cfg::P_TILE), q_lo = make_sdesc(st + 2 * cfg::P_TILE + cfg::Q_TILE);
+            // The whole warp runs the loop with warp-uniform values (descriptors stay in uniform registers);
+            // one elected lane issues the tcgen05 instructions.
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = (it + kb) % STAGES;
+                const uint32_t ph = ((it + kb) / STAGES) & 1;
+                const int cg = ch + kb / drain_kb, buf = cg % NBUF, use = cg / NBUF;
+                const bool chunk_start = (kb % drain_kb) == 0;
+                if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
+                mbar_wait(BAR(B_CONV + s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_d + (uint32_t)(buf * BN);
+                const uint32_t st = base + s * cfg::STAGE;
+                const uint64_t p_hi = make_sdesc(st), p_lo = make_sdesc(st + cfg::P_TILE);
+                const uint64_t q_hi = make_sdesc(st + 2 * cfg::P_TILE), q_lo = make_sdesc(st + 2 * cfg::P_TILE + cfg::Q_TILE);
+                const bool last_of_chunk = (kb % drain_kb) == drain_kb - 1 || kb == nkb - 1;
+                if (elect_one()) {
+                    if (trace && blockIdx.x == 0 && it + kb < 64) trace[(it + kb) * 4 + 2] = clock64();
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 floats = 32 bytes along K inside the swizzle span
@@ -207,8 +223,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                         }
                     }
                     umma_commit(BAR(B_EMPTY + s));                          // frees the stage when the MMAs retire
-                    if ((kb % drain_kb) == drain_kb - 1 || kb == nkb - 1) umma_commit(BAR(B_ACC_FULL + buf));
+                    if (last_of_chunk) umma_commit(BAR(B_ACC_FULL + buf));
+                    if (trace && blockIdx.x == 0 && it + kb < 64) trace[(it + kb) * 4 + 3] = clock64();
                 }
+                __syncwarp();
             }
         } else if (warp < 6) {
             // ------------------------------------------------------------ converters: x -> (tf32 hi, lo)
@@ -217,19 +235,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 mbar_wait(BAR(B_FULL + s), ph);
+                if (trace && blockIdx.x == 0 && ct == 0 && it + kb < 64) trace[(it + kb) * 4 + 1] = clock64();
                 uint8_t* st = gbase + s * cfg::STAGE;
-                auto convert = [&](uint8_t* hi, uint8_t* lo, int chunks) {
-#pragma unroll 4
-                    for (int c = ct; c < chunks; c += NCONV) {
-                        float4 v = *reinterpret_cast<float4*>(hi + c * 16);
-                        float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
-                        float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-                        *reinterpret_cast<float4*>(hi + c * 16) = h;
-                        *reinterpret_cast<float4*>(lo + c * 16) = l;
-                    }
-                };
-                convert(st, st + cfg::P_TILE, cfg::P_TILE / 16);
-                convert(st + 2 * cfg::P_TILE, st + 2 * cfg::P_TILE + cfg::Q_TILE, cfg::Q_TILE / 16);
+                // all of this thread's 16-byte chunks are loaded first (independent LDS in flight), then split
+                // into TF32 hi (in place) and the exact FP32 remainder lo (second tile)
+                constexpr int NP = cfg::P_TILE / 16 / NCONV, NQ = cfg::Q_TILE / 16 / NCONV;
+                float4* p_hi = reinterpret_cast<float4*>(st) + ct;
+                float4* p_lo = reinterpret_cast<float4*>(st + cfg::P_TILE) + ct;
+                float4* q_hi = reinterpret_cast<float4*>(st + 2 * cfg::P_TILE) + ct;
+                float4* q_lo = reinterpret_cast<float4*>(st + 2 * cfg::P_TILE + cfg::Q_TILE) + ct;
+                float4 v[NP + NQ];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) v[i] = p_hi[i * NCONV];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) v[NP + i] = q_hi[i * NCONV];
+#pragma unroll
+                for (int i = 0; i < NP + NQ; ++i) {
+                    const float4 x = v[i];
+                    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                    if (i < NP) { p_hi[i * NCONV] = h; p_lo[i * NCONV] = l; }
+                    else { q_hi[(i - NP) * NCONV] = h; q_lo[(i - NP) * NCONV] = l; }
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(BAR(B_CONV + s));
             }
@@ -340,6 +367,8 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t K, i
                               box_rows, /*swizzle128=*/true);
 }
 
+unsigned long long* g_trace = nullptr;
+
 template <int BN>
 static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const float* bias, const float* Cin, int64_t ldcin,
                   float* C, int64_t ldc, int P_rows, int Q_rows, int K, int transposed, int splits, int64_t split_stride,
@@ -375,11 +404,14 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const float* b
     }
     gemm_tf32x3_kernel<BN><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
                                                                 transposed, kb_per_split, split_stride, tiles_q, splits,
-                                                                n_items, mode);
+                                                                n_items, mode, g_trace);
     return check_launch("linear(tf32x3 tcgen05)");
 }
 
 }  // namespace tc
+
+// debug: per-k-block pipeline timestamps of CTA 0 (trace[kb*4 + {stage free, data landed, converted, MMAs issued}])
+void linear_tc_set_trace(unsigned long long* p) { tc::g_trace = p; }
 
 bool linear_tc_eligible(const float* A, int64_t lda, const float* W, int64_t ldw, int64_t M, int64_t N, int64_t K) {
     return ((lda & 3) == 0) && ((ldw & 3) == 0) && aligned16(A) && aligned16(W) && K >= 32 && N >= 64 &&
