@@ -104,6 +104,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 // round-to-nearest TF32 (10 explicit mantissa bits) with integer ops; the remainder x - hi is exact in FP32
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -252,10 +253,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < NP + NQ; ++i) {
                     const float4 x = v[i];
-                    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-                    const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-                    if (i < NP) { p_hi[i * NCONV] = h; p_lo[i * NCONV] = l; }
-                    else { q_hi[(i - NP) * NCONV] = h; q_lo[(i - NP) * NCONV] = l; }
+                    if (mode == 4) {
+                        // experiment: the MMA reads the raw FP32 word as TF32 (low 13 mantissa bits ignored), so only
+                        // the truncation remainder has to be written
+                        const float4 l = make_float4(x.x - tf32_trunc(x.x), x.y - tf32_trunc(x.y), x.z - tf32_trunc(x.z), x.w - tf32_trunc(x.w));
+                        if (i < NP) p_lo[i * NCONV] = l; else q_lo[(i - NP) * NCONV] = l;
+                    } else {
+                        const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                        const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+                        if (i < NP) { p_hi[i * NCONV] = h; p_lo[i * NCONV] = l; }
+                        else { q_hi[(i - NP) * NCONV] = h; q_lo[(i - NP) * NCONV] = l; }
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(BAR(B_CONV + s));

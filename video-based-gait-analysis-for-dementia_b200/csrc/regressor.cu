@@ -7,6 +7,8 @@
 // iterations, so x.W1x^T + b1 is computed once; each iteration then needs only the 157-column
 // state part.  There is no non-linearity between the layers (dropout is the identity in eval),
 // exactly as in the reference.  The three decoders are one (157,Dh) matrix.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gait {
@@ -24,6 +26,20 @@ __global__ void broadcast_state_kernel(const float* __restrict__ init, int64_t i
     state[i] = v;
 }
 
+constexpr int kDecSplits = 6;          // split-K of the 157-row decoder GEMM (only 24 output tiles otherwise)
+
+// state[f, c] += sum over split-K partials (partial 0 already holds bias); one thread per element
+__global__ void decoder_reduce_kernel(const float* __restrict__ part, int parts, int64_t part_stride,
+                                      float* __restrict__ state, int64_t F) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= F * kStateLd) return;
+    const int c = (int)(i % kStateLd);
+    if (c >= kState) return;
+    float acc = 0.f;
+    for (int p = 0; p < parts; ++p) acc += part[p * part_stride + i];
+    state[i] += acc;
+}
+
 }  // namespace gait
 
 using namespace gait;
@@ -32,7 +48,7 @@ extern "C" {
 
 size_t gait_hmr_workspace_bytes(int64_t F, int64_t Dh) {
     if (F <= 0 || Dh <= 0) return 0;
-    return (size_t)(3 * F * Dh) * sizeof(float);
+    return (size_t)(3 * F * Dh + kDecSplits * F * kStateLd) * sizeof(float);
 }
 
 int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const float* W1s, const float* b1,
@@ -54,6 +70,14 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
     float* hx = static_cast<float*>(workspace);
     float* h1 = hx + F * Dh;
     float* h2 = h1 + F * Dh;
+    float* dpart = h2 + F * Dh;                          // split-K partials of the decoder GEMM
+    // decoder GEMM (F x 157 x Dh): few output tiles, so cut K across CTAs when the tensor-core path takes it
+    int dsplits = 1;
+    if (linear_path() != 1 && linear_tc_eligible(h2, Dh, Wd, Dh, F, kState, Dh)) {
+        const int64_t nkb = ceil_div(Dh, 32);
+        dsplits = (int)std::min<int64_t>(kDecSplits, nkb);
+        while (dsplits > 1 && ceil_div(nkb, ceil_div(nkb, dsplits)) != dsplits) --dsplits;
+    }
     broadcast_state_kernel<<<(unsigned)ceil_div(F * kStateLd, 256), 256, 0, st>>>(init, init_rows, state_out, F);
     GAIT_TRY(check_launch("hmr broadcast_state"));
     if (n_iter == 0) return GAIT_OK;
@@ -62,7 +86,15 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
     for (int it = 0; it < n_iter; ++it) {
         GAIT_TRY(linear_launch(state_out, kStateLd, W1s, kStateLd, nullptr, hx, Dh, h1, Dh, F, Dh, kStateLd, st));
         GAIT_TRY(linear_launch(h1, Dh, W2, Dh, b2, nullptr, 0, h2, Dh, F, Dh, Dh, st));
-        GAIT_TRY(linear_launch(h2, Dh, Wd, Dh, bd, state_out, kStateLd, state_out, kStateLd, F, kState, Dh, st));
+        if (dsplits > 1) {
+            GAIT_TRY(linear_tc_launch(h2, Dh, Wd, Dh, bd, nullptr, 0, dpart, kStateLd, F, kState, Dh, dsplits,
+                                      F * kStateLd, st));
+            decoder_reduce_kernel<<<(unsigned)ceil_div(F * kStateLd, 256), 256, 0, st>>>(dpart, dsplits, F * kStateLd,
+                                                                                           state_out, F);
+            GAIT_TRY(check_launch("hmr decoder_reduce"));
+        } else {
+            GAIT_TRY(linear_launch(h2, Dh, Wd, Dh, bd, state_out, kStateLd, state_out, kStateLd, F, kState, Dh, st));
+        }
     }
     return GAIT_OK;
 }
