@@ -123,6 +123,11 @@ def test_linear_vs_torch_fp32(M, N, K, lib_loaded):
     dict(S=3, T=7, I=48, H=20, layers=2, bi=True),            # ragged sizes, not multiples of 4 per gate
     dict(S=4, T=6, I=3072, H=300, layers=2, bi=True),         # BidirectionalModel.rnn (gait_feat_encoder.py:51-57)
     dict(S=1, T=16, I=2048, H=2048, layers=1, bi=False),      # C1
+    dict(S=64, T=16, I=2048, H=2048, layers=1, bi=False),     # C2: persistent recurrent kernel, 128 CTAs
+    dict(S=5, T=9, I=96, H=256, layers=2, bi=True),           # persistent kernel: ragged S, reverse direction, ldy = 2H
+    dict(S=64, T=4, I=40, H=64, layers=1, bi=False),          # persistent kernel: one k-block per CTA
+    dict(S=37, T=1, I=64, H=128, layers=1, bi=False),         # single step: no recurrent GEMM at all
+    dict(S=70, T=5, I=64, H=128, layers=1, bi=False),         # S > 64: per-step path
 ])
 def test_gru_vs_torch(cfg, lib_loaded):
     from gaitb200.temporal import gru_forward
@@ -133,6 +138,36 @@ def test_gru_vs_torch(cfg, lib_loaded):
         ref, _ = gru(x.permute(1, 0, 2))
     y, _ = gru_forward(gru.cuda(), x.cuda())
     assert maxerr(y, ref.permute(1, 0, 2)) <= 2e-5
+
+
+@pytest.mark.parametrize("S,T,H,reverse", [(64, 6, 2048, 0), (9, 5, 128, 1), (3, 1, 64, 0)])
+def test_gru_layer_h0_hn_residual(S, T, H, reverse, lib_loaded):
+    """gait_gru_layer through the C ABI with an initial state, the final state and the fused residual output."""
+    L = lib_loaded
+    I = H
+    torch.manual_seed(11 + S)
+    gru = torch.nn.GRU(I, H).eval()
+    x = torch.randn(S, T, I) * 0.5
+    h0 = torch.randn(S, H) * 0.3
+    with torch.no_grad():
+        xin = x.flip(1) if reverse else x
+        ref, hn_ref = gru(xin.permute(1, 0, 2), h0[None])
+    ref = ref.permute(1, 0, 2)
+    if reverse:
+        ref = ref.flip(1)
+    xd, h0d = x.cuda(), h0.cuda()
+    w = {k: v.detach().cuda() for k, v in gru.named_parameters()}
+    y = torch.empty(S, T, H, device="cuda")
+    out = torch.empty(S, T, H, device="cuda")
+    hn = torch.empty(S, H, device="cuda")
+    nbytes = L.load().gait_gru_workspace_bytes(S, T, H)
+    ws = torch.empty(nbytes // 4 + 1, device="cuda")
+    L.call("gait_gru_layer", xd.data_ptr(), I, w["weight_ih_l0"].data_ptr(), w["weight_hh_l0"].data_ptr(),
+           w["bias_ih_l0"].data_ptr(), w["bias_hh_l0"].data_ptr(), h0d.data_ptr(), y.data_ptr(), H, xd.data_ptr(), I,
+           out.data_ptr(), H, hn.data_ptr(), S, T, I, H, reverse, ws.data_ptr(), nbytes, L.stream_ptr())
+    assert maxerr(y, ref) <= 2e-5
+    assert maxerr(out, ref + x) <= 2e-5
+    assert maxerr(hn, hn_ref[0]) <= 2e-5
 
 
 def test_temporal_encoder_variants(lib_loaded):

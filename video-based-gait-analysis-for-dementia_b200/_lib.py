@@ -35,6 +35,7 @@ _SIGS = {
     "gait_perspective_projection": [P, P, P, P, F32, F32, P, I64, I32, P],
     "gait_linear": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I64, P],
     "gait_debug_linear_trace": [P],
+    "gait_debug_gru_trace": [P],
     "gait_gru_workspace_bytes": [I64, I64, I64],
     "gait_gru_layer": [P, I64, P, P, P, P, P, P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I32, P, SZ, P],
     "gait_relu": [P, P, I64, P],

@@ -71,4 +71,14 @@ int linear_path();
 int make_tensor_map_2d(void* map, int elem_bytes, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t row_stride_bytes,
                        uint32_t box0, uint32_t box1, bool swizzle128);
 
+int make_tensor_map_3d_f32(void* map, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
+                           uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, bool swizzle128);
+// gru_rec.cu: the whole recurrence of one GRU layer/direction in one persistent cluster kernel
+bool gru_recurrent_eligible(const float* gi, const float* W_hh, const float* h0, const float* y, int64_t ldy,
+                            const float* resid, int64_t ldres, const float* out, int64_t ldout, int64_t S, int64_t T,
+                            int64_t H);
+int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, const float* h0, float* y, int64_t ldy,
+                         const float* resid, int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T,
+                         int64_t H, int reverse, unsigned int* counter, cudaStream_t stream);
+
 }  // namespace gait

@@ -5,6 +5,7 @@
 // Input projection for all S*T frames is one GEMM; the recurrence is T steps of
 // (S,H).(H,3H) plus a fused gate kernel that also emits the TemporalEncoder residual sum.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -67,7 +68,7 @@ int gait_relu(const float* x, float* y, int64_t n, gait_stream_t stream) {
 
 size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H) {
     if (S <= 0 || T <= 0 || H <= 0) return 0;
-    return (size_t)(S * T * 3 * H + kGruMaxSplits * S * 3 * H) * sizeof(float);
+    return (size_t)(S * T * 3 * H + kGruMaxSplits * S * 3 * H) * sizeof(float) + 4 * (size_t)(H / 16 + 64);   // + per-CTA step flags of the persistent kernel
 }
 
 int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* W_hh, const float* b_ih,
@@ -90,6 +91,23 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
     const int64_t F = S * T;
     // gi = x . W_ih^T + b_ih for every frame
     GAIT_TRY(linear_launch(x, ldx, W_ih, I, b_ih, nullptr, 0, gi, 3 * H, F, 3 * H, I, st));
+    // whole recurrence in one persistent cluster kernel (gru_rec.cu) when the shape allows;
+    // GAITB200_GRU_PATH=1 forces the per-step path below, =2 makes ineligibility an error
+    static int gru_path = -1;
+    if (gru_path < 0) {
+        const char* e = getenv("GAITB200_GRU_PATH");
+        gru_path = e ? atoi(e) : 0;
+    }
+    if (gru_path != 1 && linear_path() != 1) {
+        if (gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S, T, H)) {
+            unsigned int* counter = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);
+            return gru_recurrent_launch(gi, W_hh, b_hh, h0, y, ldy, resid, ldres, out, ldout, hn, S, T, H, reverse, counter, st);
+        }
+        if (gru_path == 2) {
+            set_error("gru_layer: persistent recurrent kernel not eligible for S=%lld T=%lld H=%lld", (long long)S, (long long)T, (long long)H);
+            return GAIT_ERR_UNSUPPORTED;
+        }
+    }
     const dim3 block(256), grid((unsigned)ceil_div(H, 256), (unsigned)S);
     // recurrent GEMM (S,H).(H,3H): tensor-core path with split-K so that ~all SMs get a tile
     const int64_t hstride = T * ldy;

@@ -1,0 +1,467 @@
+// The recurrence of one torch.nn.GRU layer/direction (TemporalEncoder; gait_feat_encoder.py:51-57,88) as ONE
+// persistent kernel: all T steps, the hidden-state GEMM h_{t-1}.W_hh^T on tcgen05 in FP32-accurate split-TF32
+// form, the gate math and the TemporalEncoder residual, with a grid-wide barrier between steps.
+//
+// Decomposition (H = 2048: 128 CTAs = 64 clusters of 2, one CTA per SM, all co-resident):
+//   * a cluster of KG = 2 CTAs owns 32 hidden units = 96 rows of W_hh (r, z and n gate rows of those units);
+//     CTA `kr` of the cluster contracts the K-slice [kr*H/2, (kr+1)*H/2) of those rows against the same slice of
+//     h_{t-1} for all (<= 64) sequences, so per step a CTA streams 96 x H/2 weights (L2-resident: W_hh is read
+//     T times) and only 64 x H/2 of the hidden state.
+//   * operands: A = [h_hi ; h_lo] (64 + 64 rows), B = W_hi then W_lo (96 rows): two M128 N96 K8 MMAs per k-step
+//     give h_hi.W + h_lo.W in TMEM lanes 0-63 / 64-127 (all four split products).  The tensor core truncates
+//     when it adds into its FP32 accumulator, so every 64 k the partial sum is drained (tcgen05.ld) and added
+//     round-to-nearest into FP32 registers (same scheme as linear_tc.cu).
+//   * end of step: hi + lo rows are combined through shared memory, the two K-slice partials through
+//     distributed shared memory (mbarrier handshake, no cluster-wide barrier); each CTA then finalises 16 units
+//     x 64 sequences: gates, h_t, h_t + residual, with h_{t-1} kept in registers.
+//   * h_t goes to y (the API output) and is read back by TMA at the next step.  There is no grid-wide barrier:
+//     k-block kb of a K-slice needs exactly the 32 units one cluster produces, so every CTA publishes a step
+//     flag (st.release.gpu) and the h producer polls the KG flags of that cluster (ld.acquire.gpu) before the
+//     TMA load; the W tiles of the next step are prefetched and converted while those flags are awaited.
+// Warp roles: 0 and 3 = W TMA producers (even / odd k-blocks), 1 = MMA issuer + TMEM owner, 2 = h TMA producer (polls the flags),
+// 4-11 = promotion + gates (256 threads), 12-19 = FP32 -> TF32 hi/lo converters (256 threads).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gait {
+namespace grurec {
+using namespace tcu;
+
+constexpr int KG = 2;                       // CTAs per cluster = K slices
+constexpr int UC = 16;                      // hidden units finalised per CTA
+constexpr int UPC = UC * KG;                // hidden units per cluster
+constexpr int NB = 3 * UPC;                 // W_hh rows per CTA (UMMA N) = 96
+constexpr int SB = 64;                      // sequences (A rows: 64 hi + 64 lo = UMMA M 128)
+constexpr int BK = 32;                      // floats per k-block = one 128-byte swizzle span
+constexpr int STAGES = 4;
+constexpr int H_TILE = SB * BK * 4;         //  8 192 B raw h tile (becomes the hi half)
+constexpr int A_TILE = 2 * H_TILE;          // 16 384 B
+
+constexpr int G_TILE = UPC * BK * 4;        //  4 096 B: one gate's rows = one TMA box
+constexpr int W_TILE = NB * BK * 4;         // 12 288 B
+constexpr int STAGE = A_TILE + 2 * W_TILE;  // 40 960 B: [h hi | h lo | W hi | W lo]
+constexpr int PLD = 100;                    // row stride (floats) of the partial-sum buffer: conflict-free float4 rows
+constexpr int P_FLOATS = SB * PLD;
+constexpr int NBUF = 4;                     // TMEM accumulator ring
+constexpr int TMEM_COLS = 512;              // 4 x 96 -> power of two
+constexpr int DRAIN_KB = 2;                 // k-blocks per promotion
+constexpr int NPROM = 256, NCONV = 256;
+constexpr int THREADS = 128 + NPROM + NCONV;
+constexpr int OFF_P = STAGES * STAGE;
+constexpr int OFF_BAR = OFF_P + 2 * P_FLOATS * 4;
+constexpr int SMEM = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
+
+enum : int { B_FULL_W = 0, B_FULL_H = STAGES, B_CONV = 2 * STAGES, B_EMPTY = 3 * STAGES, B_ACC_FULL = 4 * STAGES,
+             B_ACC_EMPTY = 4 * STAGES + NBUF, B_P_READY = 4 * STAGES + 2 * NBUF, B_COUNT = 4 * STAGES + 2 * NBUF + 2 };
+static_assert(B_COUNT * 8 <= 240, "barrier area");
+static_assert(UPC == BK, "one k-block of h = the units of exactly one cluster (flag indexing)");
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 split_store(float4 x, float4* lo) {
+    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+    *lo = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+    return h;
+}
+
+// debug timestamps of CTA 0: trace[step*8 + i] (step < 32) and trace[256 + kb*8 + i] for the k-blocks of step 2
+#define GRU_TRACE_STEP(i) do { if (trace && blockIdx.x == 0 && step < 32) trace[step * 8 + (i)] = clock64(); } while (0)
+#define GRU_TRACE_KB(i) do { if (trace && blockIdx.x == 0 && step == 2 && kb < 64) trace[256 + kb * 8 + (i)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(THREADS, 1)
+gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
+                     const __grid_constant__ CUtensorMap tmH0, const float* __restrict__ gi,
+                     const float* __restrict__ b_hh, const float* __restrict__ h0, float* y, int64_t ldy,
+                     const float* __restrict__ resid, int64_t ldres, float* __restrict__ out, int64_t ldout,
+                     float* __restrict__ hn, int S, int T, int H, int reverse, unsigned* flags,
+                     unsigned long long* trace) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + OFF_BAR;
+    auto BAR = [&](int i) { return bars + 8u * i; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + OFF_BAR + 240);
+    float* P = reinterpret_cast<float*>(gbase + OFF_P);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t kr = cluster_ctarank();
+    const int u0 = (blockIdx.x / KG) * UPC;            // first hidden unit of this cluster
+    const int KS = H / KG, k0 = (int)kr * KS, NKB = KS / BK;
+    const int nchunks = (NKB + DRAIN_KB - 1) / DRAIN_KB;
+    const int first_gemm = h0 ? 0 : 1;                 // h_{-1} = 0: step 0 needs no GEMM
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(BAR(B_FULL_W + s), 3);           // one 32-row box per gate, each issued by its own lane
+            mbar_init(BAR(B_FULL_H + s), 2);           // two 32-sequence boxes
+            mbar_init(BAR(B_CONV + s), NCONV / 32);       // one arrival per converter warp
+            mbar_init(BAR(B_EMPTY + s), 1);
+        }
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(BAR(B_ACC_FULL + b), 1);
+            mbar_init(BAR(B_ACC_EMPTY + b), NPROM / 32); // one arrival per promotion warp
+        }
+        mbar_init(BAR(B_P_READY + 0), KG);
+        mbar_init(BAR(B_P_READY + 1), KG);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster_sync_all();                                // peers' barriers exist before anyone arrives on them remotely
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0 || warp == 3) {
+        // ------------------------------------------------------------ W_hh tile producers (independent of h)
+        // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
+        // instruction occupies its warp for ~450 cycles (+ ~50 per extra active lane), the rows of one box are fetched
+        // one after the other (~20 cycles each), while boxes issued by different lanes / warps proceed in parallel.
+        // So: 32-row boxes, one lane per box, and two producer warps alternating k-blocks.
+        const int par = warp == 0 ? 0 : 1;
+        int it = 0;
+        for (int step = first_gemm; step < T; ++step) {
+            for (int kb = 0; kb < NKB; ++kb, ++it) {
+                if ((it & 1) != par) continue;
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+                if (lane < 3) {
+                    if (lane == 0) GRU_TRACE_KB(0);
+                    mbar_arrive_expect_tx(BAR(B_FULL_W + s), G_TILE);
+                    tma_load_2d(base + s * STAGE + A_TILE + lane * G_TILE, &tmW, k0 + kb * BK, lane * H + u0, BAR(B_FULL_W + s));
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------ h_{t-1} tile producer
+        int it = 0;
+        for (int step = first_gemm; step < T; ++step) {
+            const int t = reverse ? (T - 1 - step) : step;
+            const int tp = reverse ? t + 1 : t - 1;
+            if (step > 0) {
+                // dataflow barrier: k-block kb of this K-slice = the 32 hidden units of cluster k0/32 + kb, whose KG CTAs
+                // each publish flags[cta] = number of steps completed.  Lanes poll different k-blocks in parallel.
+                if (lane == 0) GRU_TRACE_STEP(6);
+                for (int kb = lane; kb < NKB; kb += 32) {
+                    const unsigned* fl = flags + (k0 / UPC + kb) * KG;
+                    SpinGuard guard;
+#pragma unroll
+                    for (int r = 0; r < KG; ++r)
+                        while (ld_acquire_gpu(fl + r) < (unsigned)step) guard.tick();
+                }
+                __syncwarp();
+                fence_proxy_async();                   // generic-proxy writes of h -> async-proxy (TMA) reads
+                if (lane == 0) GRU_TRACE_STEP(0);
+            }
+            // four lanes issue the 2 x 2 boxes (32 sequences each) of two k-blocks at a time
+            for (int kb0 = 0; kb0 < NKB; kb0 += 2) {
+                const int kb = kb0 + (lane >> 1), half = lane & 1;
+                if (lane < 4 && kb < NKB) {
+                    const int my = it + (lane >> 1), s = my % STAGES;
+                    const uint32_t ph = (my / STAGES) & 1;
+                    mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+                    if (half == 0) GRU_TRACE_KB(1);
+                    mbar_arrive_expect_tx(BAR(B_FULL_H + s), H_TILE / 2);
+                    const uint32_t dst = base + s * STAGE + half * (H_TILE / 2);
+                    if (step == 0) tma_load_3d(dst, &tmH0, k0 + kb * BK, 0, half * (SB / 2), BAR(B_FULL_H + s));
+                    else tma_load_3d(dst, &tmY, k0 + kb * BK, tp, half * (SB / 2), BAR(B_FULL_H + s));
+                }
+                __syncwarp();
+                it += min(2, NKB - kb0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
+        constexpr uint32_t idesc = umma_idesc_tf32(128, NB);
+        int it = 0, ch = 0;
+        for (int step = first_gemm; step < T; ++step) {
+            for (int kb = 0; kb < NKB; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int cg = ch + kb / DRAIN_KB, buf = cg % NBUF, use = cg / NBUF;
+                const bool chunk_start = (kb % DRAIN_KB) == 0;
+                if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
+                mbar_wait(BAR(B_CONV + s), ph);
+                tc_fence_after();
+                const uint32_t acc = tmem_d + (uint32_t)(buf * NB);
+                const uint32_t st = base + s * STAGE;
+                const uint64_t a = make_sdesc_sw128(st);
+                const uint64_t b_hi = make_sdesc_sw128(st + A_TILE), b_lo = make_sdesc_sw128(st + A_TILE + W_TILE);
+                const bool last_of_chunk = (kb % DRAIN_KB) == DRAIN_KB - 1 || kb == NKB - 1;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                        umma_tf32(acc, a + adv, b_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                        umma_tf32(acc, a + adv, b_lo + adv, idesc, 1u);
+                    }
+                    umma_commit(BAR(B_EMPTY + s));
+                    if (last_of_chunk) umma_commit(BAR(B_ACC_FULL + buf));
+                    GRU_TRACE_KB(7);
+                    if (kb == NKB - 1) GRU_TRACE_STEP(2);
+                }
+                __syncwarp();
+            }
+            ch += nchunks;
+        }
+    } else if (warp >= 12) {
+        // ------------------------------------------------------------ converters: x -> (tf32 hi in place, lo)
+        const int ct = threadIdx.x - (128 + NPROM);
+        int it = 0;
+        for (int step = first_gemm; step < T; ++step) {
+            for (int kb = 0; kb < NKB; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                uint8_t* st = gbase + s * STAGE;
+                float4* w_hi = reinterpret_cast<float4*>(st + A_TILE) + ct;
+                float4* w_lo = reinterpret_cast<float4*>(st + A_TILE + W_TILE) + ct;
+                float4* h_hi = reinterpret_cast<float4*>(st) + ct;
+                float4* h_lo = reinterpret_cast<float4*>(st + H_TILE) + ct;
+                constexpr int NW = W_TILE / 16 / NCONV, NH = H_TILE / 16 / NCONV;   // 3, 2
+                mbar_wait(BAR(B_FULL_W + s), ph);
+                if (ct == 0) GRU_TRACE_KB(4);
+                float4 v[NW];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) v[i] = w_hi[i * NCONV];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) w_hi[i * NCONV] = split_store(v[i], &w_lo[i * NCONV]);
+                mbar_wait(BAR(B_FULL_H + s), ph);
+                if (ct == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
+                float4 u[NH];
+#pragma unroll
+                for (int i = 0; i < NH; ++i) u[i] = h_hi[i * NCONV];
+#pragma unroll
+                for (int i = 0; i < NH; ++i) h_hi[i * NCONV] = split_store(u[i], &h_lo[i * NCONV]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_CONV + s));
+                if (ct == 0) GRU_TRACE_KB(6);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ promotion + gates
+        const int pt = threadIdx.x - 128;
+        const int q = warp & 3;                            // TMEM lane quadrant of this warp
+        const int hf = (warp - 4) >> 2;                    // which 48 of the 96 accumulator columns
+        const int prow = (q * 32 + lane) & 63;             // sequence of this thread's TMEM lane (lanes 64+ = lo rows)
+        // finalisation: thread -> (sequence, 4 consecutive hidden units)
+        const int seq = pt >> 2, u4 = pt & 3;
+        const int ucol = (int)kr * UC + u4 * 4;            // column inside a gate's 32-wide block of P
+        const int unit = u0 + ucol;
+        const bool act = seq < S;
+        float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act && h0) hp = *reinterpret_cast<const float4*>(h0 + (int64_t)seq * H + unit);
+        const float4 br = *reinterpret_cast<const float4*>(b_hh + unit);
+        const float4 bz = *reinterpret_cast<const float4*>(b_hh + H + unit);
+        const float4 bn = *reinterpret_cast<const float4*>(b_hh + 2 * H + unit);
+        int ch = 0, gstep = 0;
+        for (int step = 0; step < T; ++step) {
+            const int t = reverse ? (T - 1 - step) : step;
+            const int64_t f = (int64_t)seq * T + t;
+            float4 ar = br, az = bz, an = make_float4(0.f, 0.f, 0.f, 0.f), rs = an;
+            if (act) {                                     // issued before the GEMM of this step completes
+                const float* g = gi + f * 3 * H + unit;
+                ar = f4_add(ar, *reinterpret_cast<const float4*>(g));
+                az = f4_add(az, *reinterpret_cast<const float4*>(g + H));
+                an = *reinterpret_cast<const float4*>(g + 2 * H);
+                if (out) rs = *reinterpret_cast<const float4*>(resid + f * ldres + unit);
+            }
+            float4 sr = make_float4(0.f, 0.f, 0.f, 0.f), sz = sr, sn = sr;
+            if (step >= first_gemm) {
+                float acc[NB / 2];
+#pragma unroll
+                for (int j = 0; j < NB / 2; ++j) acc[j] = 0.f;
+                for (int chunk = 0; chunk < nchunks; ++chunk) {
+                    const int cg = ch + chunk, buf = cg % NBUF, use = cg / NBUF;
+                    mbar_wait(BAR(B_ACC_FULL + buf), use & 1);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NB + hf * (NB / 2));
+#pragma unroll
+                    for (int c = 0; c < NB / 32; ++c) {
+                        uint32_t r[16];
+                        tmem_ld16_nowait(ta + c * 16, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[c * 16 + j] += __uint_as_float(r[j]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + buf));
+                }
+                ch += nchunks;
+                if (pt == 0) GRU_TRACE_STEP(3);
+                // hi rows + lo rows -> this CTA's K-slice partial P[seq][96]
+                float* Pb = P + (gstep & 1) * P_FLOATS;
+                float4* prow4 = reinterpret_cast<float4*>(Pb + prow * PLD + hf * (NB / 2));
+                if (q >= 2) {
+#pragma unroll
+                    for (int j = 0; j < NB / 8; ++j) prow4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                }
+                named_bar_sync(1, NPROM);
+                if (q < 2) {
+#pragma unroll
+                    for (int j = 0; j < NB / 8; ++j) {
+                        const float4 o = prow4[j];
+                        prow4[j] = make_float4(o.x + acc[4 * j], o.y + acc[4 * j + 1], o.z + acc[4 * j + 2], o.w + acc[4 * j + 3]);
+                    }
+                }
+                named_bar_sync(1, NPROM);
+                // tell every CTA of the cluster (incl. this one) that this partial is complete, wait for all
+                const uint32_t pbar = BAR(B_P_READY + (gstep & 1));
+                if (pt == 0) {
+#pragma unroll
+                    for (uint32_t rr = 0; rr < (uint32_t)KG; ++rr) mbar_arrive_remote_release(map_to_rank(pbar, rr));
+                }
+                mbar_wait_cluster(pbar, (gstep >> 1) & 1);
+                if (pt == 0) GRU_TRACE_STEP(4);
+                const uint32_t pa = smem_u32(Pb + seq * PLD + ucol);
+#pragma unroll
+                for (uint32_t rr = 0; rr < (uint32_t)KG; ++rr) {
+                    const uint32_t ra = map_to_rank(pa, rr);
+                    sr = f4_add(sr, ld_cluster_f4(ra));
+                    sz = f4_add(sz, ld_cluster_f4(ra + UPC * 4));
+                    sn = f4_add(sn, ld_cluster_f4(ra + 2 * UPC * 4));
+                }
+                ++gstep;
+            }
+            float4 h;
+            {
+                const float r0 = sigmoidf_(ar.x + sr.x), r1 = sigmoidf_(ar.y + sr.y), r2 = sigmoidf_(ar.z + sr.z), r3 = sigmoidf_(ar.w + sr.w);
+                const float z0 = sigmoidf_(az.x + sz.x), z1 = sigmoidf_(az.y + sz.y), z2 = sigmoidf_(az.z + sz.z), z3 = sigmoidf_(az.w + sz.w);
+                const float n0 = tanhf(an.x + r0 * (sn.x + bn.x)), n1 = tanhf(an.y + r1 * (sn.y + bn.y));
+                const float n2 = tanhf(an.z + r2 * (sn.z + bn.z)), n3 = tanhf(an.w + r3 * (sn.w + bn.w));
+                h = make_float4((1.f - z0) * n0 + z0 * hp.x, (1.f - z1) * n1 + z1 * hp.y, (1.f - z2) * n2 + z2 * hp.z,
+                                (1.f - z3) * n3 + z3 * hp.w);
+            }
+            hp = h;
+            if (act) {
+                *reinterpret_cast<float4*>(y + f * ldy + unit) = h;
+                if (out) *reinterpret_cast<float4*>(out + f * ldout + unit) = f4_add(h, rs);
+                if (hn && step == T - 1) *reinterpret_cast<float4*>(hn + (int64_t)seq * H + unit) = h;
+            }
+            if (step < T - 1) {
+                fence_proxy_async_global();
+                named_bar_sync(1, NPROM);
+                if (pt == 0) st_release_gpu(flags + blockIdx.x, (unsigned)(step + 1));
+            }
+            if (pt == 0) GRU_TRACE_STEP(5);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+    cluster_sync_all();                                // nobody leaves while a peer may still read its partials
+}
+
+unsigned long long* g_trace = nullptr;
+
+static int max_coresident_ctas() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    int n_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * KG);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = KG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaFuncSetAttribute(gru_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n_clusters, gru_recurrent_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n_clusters = 0;
+    }
+    cached = n_clusters * KG;
+    return cached;
+}
+
+}  // namespace grurec
+
+bool gru_recurrent_eligible(const float* gi, const float* W_hh, const float* h0, const float* y, int64_t ldy,
+                            const float* resid, int64_t ldres, const float* out, int64_t ldout, int64_t S, int64_t T,
+                            int64_t H) {
+    using namespace grurec;
+    if (S < 1 || S > SB || T < 1 || T > 32768) return false;
+    if (H % (BK * KG) != 0 || H % UPC != 0) return false;
+    if (!aligned16(gi) || !aligned16(W_hh) || !aligned16(y) || (ldy & 3)) return false;
+    if (h0 && !aligned16(h0)) return false;
+    if (out && (!aligned16(out) || !aligned16(resid) || (ldout & 3) || (ldres & 3))) return false;
+    return H / UC <= max_coresident_ctas();
+}
+
+int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, const float* h0, float* y, int64_t ldy,
+                         const float* resid, int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T,
+                         int64_t H, int reverse, unsigned int* counter, cudaStream_t stream) {
+    using namespace grurec;
+    GAIT_REQUIRE(aligned16(b_hh) && (!hn || aligned16(hn)), "gru(persistent): b_hh / hn must be 16-byte aligned");
+    CUtensorMap tmW, tmY, tmH0;
+    GAIT_TRY(make_tensor_map_2d(&tmW, 4, W_hh, (uint64_t)H, (uint64_t)(3 * H), (uint64_t)H * 4, BK, UPC, true));
+    GAIT_TRY(make_tensor_map_3d_f32(&tmY, y, (uint64_t)H, (uint64_t)T, (uint64_t)S, (uint64_t)ldy * 4, (uint64_t)(T * ldy) * 4,
+                                    BK, 1, SB / 2, true));
+    if (h0) GAIT_TRY(make_tensor_map_3d_f32(&tmH0, h0, (uint64_t)H, 1, (uint64_t)S, (uint64_t)H * 4, (uint64_t)H * 4, BK, 1, SB / 2, true));
+    else tmH0 = tmY;
+    GAIT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * (size_t)(H / UC), stream));   // per-CTA step flags
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(H / UC));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = KG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at;
+    // cooperative launch guarantees the co-residency the grid barrier relies on; if the runtime refuses the
+    // cluster + cooperative combination, the occupancy check in gru_recurrent_eligible() is the guarantee.
+    static int coop = -1;
+    if (coop < 0) {
+        const char* e = getenv("GAITB200_GRU_COOP");      // 0: plain cluster launch (e.g. under a profiler)
+        coop = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    cfg.numAttrs = coop ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gru_recurrent_kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out,
+                                       ldout, hn, (int)S, (int)T, (int)H, reverse, counter, g_trace);
+    if (e != cudaSuccess && coop) {
+        cudaGetLastError();
+        coop = 0;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, gru_recurrent_kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out, ldout,
+                               hn, (int)S, (int)T, (int)H, reverse, counter, g_trace);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("gru(persistent): launch failed: %s", cudaGetErrorString(e));
+        return GAIT_ERR_CUDA;
+    }
+    return check_launch("gru(persistent recurrent)");
+}
+
+}  // namespace gait
+
+// Debug hook: device buffer of 512 uint64 that receives CTA 0's per-step and per-k-block (step 2) clock64 stamps
+// of subsequent persistent-GRU launches; NULL disables.
+extern "C" int gait_debug_gru_trace(unsigned long long* device_buffer) {
+    gait::grurec::g_trace = device_buffer;
+    return GAIT_OK;
+}

@@ -155,7 +155,7 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(FULL(s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(FULL(s)) : "memory");   // two issuing lanes
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(s)) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(s)), "r"(128) : "memory");
         }
@@ -172,7 +172,7 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == NCOMPUTE / 32) {
-        // ---------------------------------------------------------------- producer (warp-uniform loop, one lane issues)
+        // ---------------------------------------------------------------- producer (warp-uniform loop, one lane per copy)
         int cur_tile = -1, tile = tile_lo, g = g_lo;
         for (int n = 0; n < item_hi - item_lo; ++n) {
             const int s = n % NS;
@@ -182,17 +182,20 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             // n-1, whose stage is released only after its accumulator was consumed
             if (new_tile && cur_tile >= 0) mbar_wait(EMPTY((n - 1) % NS), ((n - 1) / NS) & 1);
             const uint32_t st = smem_u32(smem + OFF_STAGE + s * STAGE);
-            if (elect_one()) {
-                if (new_tile) {
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(WFULL), "r"((uint32_t)W_BLOB) : "memory");
-                    bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, WFULL);
-                }
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)STAGE) : "memory");
+            // A thread's TMA operations execute one after the other (~500 cycles each, scripts/microbench/tma_issue.cu);
+            // different lanes overlap, so each copy of an item is issued by its own lane.
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)A_BLOB) : "memory");
                 bulk_g2s(st, Aop + (int64_t)g * (A_BLOB / 4), A_BLOB, FULL(s));
+            } else if (lane == 1) {
                 // 8 rows x 1536 B of v_posed as one 2D tensor copy (64-bit elements; rows past F read as zero)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)(FT * V_ROW)) : "memory");
                 asm volatile(
                     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                     ::"r"(st + A_BLOB), "l"(reinterpret_cast<uint64_t>(&tmV)), "r"(tile * (VT * 3 / 2)), "r"(g * FT), "r"(FULL(s)) : "memory");
+            } else if (lane == 2 && new_tile) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(WFULL), "r"((uint32_t)W_BLOB) : "memory");
+                bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, WFULL);
             }
             __syncwarp();
             cur_tile = tile;

@@ -31,8 +31,9 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int MAX_STAGES = 4;
+constexpr int BOX_ROWS = 32;               // rows per TMA box: the rows of a box are fetched serially, boxes in parallel
 constexpr int DRAIN_KB = 2;               // k-blocks accumulated in TMEM between promotions to FP32 registers
-constexpr int THREADS = 320;              // warp0 TMA, warp1 MMA/TMEM, warps 2-5 convert, warps 6-9 promote + epilogue
+constexpr int THREADS = 352;              // warp0 + warp10 TMA (even / odd k-blocks), warp1 MMA/TMEM, warps 2-5 convert, warps 6-9 promote + epilogue
 constexpr int NCONV = 128;
 constexpr int NDRAIN = 128;
 
@@ -146,13 +147,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(BAR(B_FULL + s), 1);
-            mbar_init(BAR(B_CONV + s), NCONV);
+            mbar_init(BAR(B_FULL + s), (BM + BN) / BOX_ROWS);   // one arrival per 32-row TMA box
+            mbar_init(BAR(B_CONV + s), NCONV / 32);        // one arrival per converter warp
             mbar_init(BAR(B_EMPTY + s), 1);
         }
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(BAR(B_ACC_FULL + b), 1);
-            mbar_init(BAR(B_ACC_EMPTY + b), NDRAIN);
+            mbar_init(BAR(B_ACC_EMPTY + b), NDRAIN / 32);  // one arrival per promotion warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -176,18 +177,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const int nkb = min(kb_per_split, nkb_total - kb0);
         const int nchunks = (nkb + drain_kb - 1) / drain_kb;
 
-        if (warp == 0) {
-            // ------------------------------------------------------------ TMA producer
+        if (warp == 0 || warp == 10) {
+            // ------------------------------------------------------------ TMA producers
+            // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
+            // instruction occupies its warp for ~450 cycles (+ ~50 per extra active lane), the rows of one box are
+            // fetched one after the other, boxes issued by different lanes / warps proceed in parallel.  So the two
+            // tiles of a k-block are cut into 32-row boxes, one lane each, and two producer warps alternate k-blocks.
+            const int par = warp == 0 ? 0 : 1;
+            constexpr int PB = BM / BOX_ROWS, QB = BN / BOX_ROWS;
             for (int kb = 0; kb < nkb; ++kb) {
+                if (((it + kb) & 1) != par) continue;
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
                 const uint32_t st = base + s * cfg::STAGE;
-                if (elect_one()) {
-                    if (trace && blockIdx.x == 0 && it + kb < 64) trace[(it + kb) * 4 + 0] = clock64();
-                    mbar_arrive_expect_tx(BAR(B_FULL + s), cfg::P_TILE + cfg::Q_TILE);
-                    tma_load_2d(st, &tmP, (kb0 + kb) * BK, p0, BAR(B_FULL + s));
-                    tma_load_2d(st + 2 * cfg::P_TILE, &tmQ, (kb0 + kb) * BK, q0, BAR(B_FULL + s));
+                if (lane < PB + QB) {
+                    if (trace && blockIdx.x == 0 && lane == 0 && it + kb < 64) trace[(it + kb) * 4 + 0] = clock64();
+                    mbar_arrive_expect_tx(BAR(B_FULL + s), BOX_ROWS * BK * 4);
+                    if (lane < PB) tma_load_2d(st + lane * (BOX_ROWS * BK * 4), &tmP, (kb0 + kb) * BK, p0 + lane * BOX_ROWS, BAR(B_FULL + s));
+                    else tma_load_2d(st + 2 * cfg::P_TILE + (lane - PB) * (BOX_ROWS * BK * 4), &tmQ, (kb0 + kb) * BK, q0 + (lane - PB) * BOX_ROWS, BAR(B_FULL + s));
                 }
                 __syncwarp();
             }
@@ -229,7 +237,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 }
                 __syncwarp();
             }
-        } else if (warp < 6) {
+        } else if (warp >= 2 && warp < 6) {
             // ------------------------------------------------------------ converters: x -> (tf32 hi, lo)
             const int ct = threadIdx.x - 64;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -253,7 +261,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < NP + NQ; ++i) {
                     const float4 x = v[i];
-                    if (mode == 4) {
+                    if (mode == 5) {
+                        // the MMA reads the raw FP32 word as TF32 (low 13 mantissa bits ignored = truncation), so hi needs
+                        // no write; lo = round-to-nearest-TF32 of the exact truncation remainder: |x - hi - lo| <= 2^-22 |x|
+                        const float4 l = make_float4(tf32_hi(x.x - tf32_trunc(x.x)), tf32_hi(x.y - tf32_trunc(x.y)),
+                                                     tf32_hi(x.z - tf32_trunc(x.z)), tf32_hi(x.w - tf32_trunc(x.w)));
+                        if (i < NP) p_lo[i * NCONV] = l; else q_lo[(i - NP) * NCONV] = l;
+                    } else if (mode == 4) {
                         // experiment: the MMA reads the raw FP32 word as TF32 (low 13 mantissa bits ignored), so only
                         // the truncation remainder has to be written
                         const float4 l = make_float4(x.x - tf32_trunc(x.x), x.y - tf32_trunc(x.y), x.z - tf32_trunc(x.z), x.w - tf32_trunc(x.w));
@@ -266,9 +280,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(BAR(B_CONV + s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_CONV + s));
             }
-        } else {
+        } else if (warp >= 6 && warp < 10) {
             // ------------------------------------------------------------ promotion + epilogue
             // The tensor core adds into its FP32 accumulator with truncation, so error grows linearly
             // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every DRAIN_KB
@@ -289,7 +304,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     for (int j = 0; j < 32; ++j) accr[c * 32 + j] += __uint_as_float(r[j]);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(BAR(B_ACC_EMPTY + buf));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + buf));
             }
             const int prow = p0 + quad * 32 + lane;
             const bool first_split = z == 0;
@@ -370,7 +386,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------ host
-static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t K, int64_t ld, int /*tile_rows*/) {
+    const int box_rows = BOX_ROWS;
     return make_tensor_map_2d(m, /*elem_bytes=*/4, ptr, (uint64_t)K, (uint64_t)rows, (uint64_t)ld * sizeof(float), BK,
                               box_rows, /*swizzle128=*/true);
 }
