@@ -75,6 +75,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
+// same with the M-side operand read from tensor memory (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+
 // Offset (in floats) of element (row, k) inside one hi/lo part of a core-matrix blob with `rows` rows.
 __host__ __device__ __forceinline__ int blob_index(int rows, int row, int k) {
     return ((k >> 2) * (rows >> 3) + (row >> 3)) * 32 + (row & 7) * 4 + (k & 3);
@@ -102,16 +117,19 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
 //                              (= vertices): tcgen05.ld T for 8 frames, apply to v_posed in smem, fused
 //                              regressor-row partial, coalesced stores, then release the stage
 // Loads run up to 3 items ahead and two epilogues are in flight, which hides the TMA/HBM/TMEM latencies.
-constexpr int NS = 5;                                    // stages = TMEM accumulator buffers (5 x 96 = 480 columns)
+constexpr int NS = 6;                                    // shared-memory stages: ~180 KB of loads in flight per SM (HBM latency)
+constexpr int NACC = 4;                                  // TMEM accumulator buffers (4 x 96 = 384 columns)
 constexpr int NG = 3;                                    // consumer groups
 constexpr int STAGE = A_BLOB + FT * V_ROW;               // 30 720 B
-constexpr int OFF_STAGE = W_BLOB;
+constexpr int OFF_STAGE = 0;
 constexpr int OFF_JX = OFF_STAGE + NS * STAGE;           // NG x 128 floats of the fused regressor row
 constexpr int OFF_BAR = OFF_JX + NG * VT * 4;
-constexpr int SMEM3 = OFF_BAR + 192;
-constexpr int TMEM_COLS3 = 512;                          // NS x 96 columns -> 512 (power of two)
+constexpr int SMEM3 = OFF_BAR + 256;
+constexpr int TMEM_COLS3 = 512;                          // 384 accumulator columns + 2 x 48 weight columns -> 512
+constexpr int TMEM_W = NACC * NCOL;                      // first column of the weight operand: 2 buffers x [hi 24 | lo 24]
+constexpr int W_COLS = 2 * NJ;
 constexpr int NCOMPUTE = NG * 128;
-constexpr int THREADS3 = NCOMPUTE + 64;
+constexpr int THREADS3 = NCOMPUTE + 64 + 128;            // + producer warp, MMA warp, weight-loader warpgroup
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -142,10 +160,12 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto FULL = [&](int s) { return bar0 + 8u * s; };               // TMA landed (tx count)
-    auto MMAD = [&](int s) { return bar0 + 8u * (NS + s); };        // accumulator ready
-    auto EMPTY = [&](int s) { return bar0 + 8u * (2 * NS + s); };   // consumer group done with the stage
-    const uint32_t WFULL = bar0 + 8u * (3 * NS);                    // weight blob landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (3 * NS + 1));
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NS + s); };       // consumer group done with the stage
+    auto MMAD = [&](int a) { return bar0 + 8u * (2 * NS + a); };    // accumulator a ready
+    auto ACCFREE = [&](int a) { return bar0 + 8u * (2 * NS + NACC + a); };   // accumulator a has been read out
+    auto WFULL = [&](int b) { return bar0 + 8u * (2 * NS + 2 * NACC + b); };     // weight tile b is in tensor memory
+    auto WFREE = [&](int b) { return bar0 + 8u * (2 * NS + 2 * NACC + 2 + b); }; // the MMAs that read weight buffer b have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NS + 2 * NACC + 4));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // contiguous, balanced item range of this CTA; item = tile * groups + group
@@ -156,10 +176,16 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(FULL(s)) : "memory");   // two issuing lanes
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(s)) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(s)), "r"(128) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(s)), "r"(4) : "memory");    // one arrival per consumer warp
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WFULL) : "memory");
+        for (int a = 0; a < NACC; ++a) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(a)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ACCFREE(a)), "r"(4) : "memory");
+        }
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(WFULL(b)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WFREE(b)) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NCOMPUTE / 32 + 1) {
@@ -173,14 +199,10 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
 
     if (warp == NCOMPUTE / 32) {
         // ---------------------------------------------------------------- producer (warp-uniform loop, one lane per copy)
-        int cur_tile = -1, tile = tile_lo, g = g_lo;
+        int tile = tile_lo, g = g_lo;
         for (int n = 0; n < item_hi - item_lo; ++n) {
             const int s = n % NS;
             if (n >= NS) mbar_wait(EMPTY(s), ((n / NS) - 1) & 1);
-            const bool new_tile = tile != cur_tile;
-            // the previous tile's MMAs (which read the weight blob) must have retired: its last item is
-            // n-1, whose stage is released only after its accumulator was consumed
-            if (new_tile && cur_tile >= 0) mbar_wait(EMPTY((n - 1) % NS), ((n - 1) / NS) & 1);
             const uint32_t st = smem_u32(smem + OFF_STAGE + s * STAGE);
             // A thread's TMA operations execute one after the other (~500 cycles each, scripts/microbench/tma_issue.cu);
             // different lanes overlap, so each copy of an item is issued by its own lane.
@@ -193,48 +215,77 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                 asm volatile(
                     "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                     ::"r"(st + A_BLOB), "l"(reinterpret_cast<uint64_t>(&tmV)), "r"(tile * (VT * 3 / 2)), "r"(g * FT), "r"(FULL(s)) : "memory");
-            } else if (lane == 2 && new_tile) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(WFULL), "r"((uint32_t)W_BLOB) : "memory");
-                bulk_g2s(smem_u32(smem), Wpack + (int64_t)tile * (W_BLOB / 4), W_BLOB, WFULL);
             }
             __syncwarp();
-            cur_tile = tile;
             if (++g == groups) { g = 0; ++tile; }
+        }
+    } else if (warp >= NCOMPUTE / 32 + 2) {
+        // ---------------------------------------------------------------- weight loader: vertex tile -> tensor memory
+        // The skinning weights are the M-side operand of every MMA of a vertex tile (~46 work items per CTA), so
+        // they live in tensor memory (lane = vertex, columns [hi 24 | lo 24]) instead of being re-read from shared
+        // memory by each of the 9 MMAs of each item.  Two buffers: the next tile is loaded while the current one is used.
+        const int row = (warp & 3) * 32 + lane;                    // TMEM lane = vertex within the tile
+        const int tile_hi = (item_hi - 1) / groups;
+        for (int tile = tile_lo, i = 0; tile <= tile_hi && item_hi > item_lo; ++tile, ++i) {
+            const int b = i & 1;
+            if (i >= 2) mbar_wait(WFREE(b), ((i >> 1) - 1) & 1);
+            const float* blob = Wpack + (int64_t)tile * (W_BLOB / 4);
+            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(TMEM_W + b * W_COLS);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+#pragma unroll
+                for (int c = 0; c < NJ / 8; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = blob[part * (W_PART / 4) + blob_index(VT, row, c * 8 + k)];
+                    tmem_st8(ta + part * NJ + c * 8, v);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(WFULL(b));
         }
     } else if (warp == NCOMPUTE / 32 + 1) {
         // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
-        constexpr uint32_t W_LBO = VT * 16, A_LBO = NCOL * 16, SBO = 128;
-        const uint32_t w_hi = smem_u32(smem), w_lo = w_hi + W_PART;
-        int cur_tile = -1, wuse = 0, tile = tile_lo, g = g_lo;
-        for (int n = 0; n < item_hi - item_lo; ++n) {
+        constexpr uint32_t A_LBO = NCOL * 16, SBO = 128;
+        int cur_tile = -1, widx = -1, tile = tile_lo, g = g_lo;
+        const int n_total = item_hi - item_lo;
+        for (int n = 0; n < n_total; ++n) {
             const int s = n % NS;
             if (tile != cur_tile) {
-                mbar_wait(WFULL, wuse & 1);
+                ++widx;
+                mbar_wait(WFULL(widx & 1), (widx >> 1) & 1);
                 cur_tile = tile;
-                ++wuse;
             }
+            const int a = n % NACC;
+            if (n >= NACC) mbar_wait(ACCFREE(a), ((n / NACC) - 1) & 1);
             mbar_wait(FULL(s), (n / NS) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = smem_u32(smem + OFF_STAGE + s * STAGE), a_lo = a_hi + A_PART;
-            const uint32_t acc = tmem_d + (uint32_t)(s * NCOL);
+            const uint32_t acc = tmem_d + (uint32_t)(a * NCOL);
+            const uint32_t w_hi = tmem_d + (uint32_t)(TMEM_W + (widx & 1) * W_COLS), w_lo = w_hi + NJ;
+            const bool last_of_tile = (g + 1 == groups) || (n + 1 == n_total);
             if (elect_one()) {
-                // D[128 x 96] = W(128 x 24) . Aop(96 x 24)^T, split-TF32: small cross terms first
+                // D[128 x 96] = W(128 x 24, tensor memory) . Aop(96 x 24, shared memory)^T, split-TF32: small cross terms first
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
                     for (int ks = 0; ks < NJ / 8; ++ks) {
-                        const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 2 * ks * W_LBO;
+                        const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 8 * ks;
                         const uint32_t ao = (pass == 1 ? a_lo : a_hi) + 2 * ks * A_LBO;
-                        umma_tf32(acc, make_desc(wo, W_LBO, SBO), make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
+                        umma_tf32_ts(acc, wo, make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
                     }
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(s)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(a)) : "memory");
+                if (last_of_tile)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(WFREE(widx & 1)) : "memory");
             }
             __syncwarp();
             if (++g == groups) { g = 0; ++tile; }
         }
-    } else {
+    } else if (warp < NCOMPUTE / 32) {
         // ---------------------------------------------------------------- consumer groups
         const int grp = warp >> 2, quad = warp & 3;                // group, TMEM lane quarter
         const int gt = tid & 127;                                  // thread within the group = vertex within the tile
@@ -252,14 +303,15 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                 sJx[gt] = (gt < nv) ? jx[v0 + gt] : 0.f;
                 cur_tile = tile;
             }
+            const int a = n % NACC;
             mbar_wait(FULL(s), ph);                                // v_posed rows visible
-            mbar_wait(MMAD(s), ph);
+            mbar_wait(MMAD(a), (n / NACC) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {
                 // all 96 accumulator columns of this vertex and its 8 v_posed entries are fetched up front
                 // (one TMEM round trip, one smem round trip), then 8 independent 3x4 applies
                 uint32_t t[NCOL];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * NCOL);
+                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * NCOL);
                 tmem_ld32_nowait(taddr, t);
                 tmem_ld32_nowait(taddr + 32, t + 32);
                 tmem_ld32_nowait(taddr + 64, t + 64);
@@ -268,6 +320,9 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
 #pragma unroll
                 for (int f = 0; f < FT; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ACCFREE(a));            // the accumulator can take the MMAs of item n + NACC
 #pragma unroll
                 for (int f = 0; f < FT; ++f) {
                     const uint32_t* q = t + f * 12;
@@ -314,7 +369,8 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic accesses precede the stage's TMA refill
-            mbar_arrive(EMPTY(s));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(EMPTY(s));
             g += NG;
             while (g >= groups) { g -= groups; ++tile; }
         }
