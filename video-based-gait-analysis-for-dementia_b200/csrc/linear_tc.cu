@@ -5,10 +5,16 @@
 // Both operands are K-major FP32 in global memory (torch Linear / GRU layout).  Per k-block of 32
 // floats (= one 128-byte swizzle span) the pipeline is
 //
-//   TMA producer (1 thread)      cp.async.bulk.tensor 2D, SWIZZLE_128B  -> raw P/Q tiles in smem
-//   converter warps (4 warps)    x -> hi = rna_tf32(x) (in place), lo = x - hi (second tile);
-//                                elementwise, so the TMA swizzle pattern is preserved
-//   MMA issuer (1 thread)        per 8-wide k-step three tcgen05.mma.kind::tf32 into one TMEM
+//   TMA producers (2 warps)      cp.async.bulk.tensor 2D, SWIZZLE_128B, 32-row boxes, one lane per box -> raw P/Q tiles
+//   converter warps (4 warps)    split x = hi + lo with hi = the raw FP32 word (the tensor core ignores the low 13
+//                                mantissa bits = truncation) and lo = RN_tf32(x - trunc(x)): |x - hi - lo| <= 2^-22 |x|.
+//                                P (the 128-row operand): each thread moves its row from smem into TENSOR MEMORY
+//                                (tcgen05.st: columns [hi 32 | lo 32] of the stage), so the MMAs read it from TMEM and
+//                                neither P_hi nor P_lo is ever written to or re-read from shared memory;
+//                                Q: only the lo tile is written (elementwise, so the TMA swizzle pattern is preserved).
+//                                Shared-memory bandwidth (LDS/STS + UMMA operand reads share one 128 B/clk pipe,
+//                                ncu: 97 % busy before this change) is what bounds this kernel, not the tensor pipe.
+//   MMA issuer (1 thread)        per 8-wide k-step three tcgen05.mma.kind::tf32 (A operand in TMEM) into one TMEM
 //                                accumulator: P_lo.Q_hi + P_hi.Q_lo + P_hi.Q_hi
 //   promotion warps (4 warps)     every 2 k-blocks: tcgen05.ld 32x32b of the TMEM partial sum, added
 //                                (round-to-nearest) into FP32 registers; two TMEM buffers alternate.
@@ -41,12 +47,16 @@ template <int BN>
 struct Cfg {
     static constexpr int P_TILE = BM * BK * 4;
     static constexpr int Q_TILE = BN * BK * 4;
-    static constexpr int STAGE = 2 * P_TILE + 2 * Q_TILE;     // [P hi][P lo][Q hi][Q lo]
-    static constexpr int STAGES = (BN <= 64) ? 4 : 3;         // 4 x 48 KB or 3 x 64 KB
+    static constexpr int STAGE = P_TILE + 2 * Q_TILE;         // [P raw][Q raw = hi][Q lo]
+    static constexpr int STAGES = 4;                          // 4 x 32 KB (BN 64) or 4 x 48 KB (BN 128)
     static constexpr int STAGING = 4 * 32 * 36 * 4;
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM = STAGES * STAGE + STAGING + BAR_BYTES + 1024;   // +1024 alignment slack
-    static constexpr int TMEM_COLS = 4 * BN;                  // ring of four accumulator buffers
+    static constexpr int NBUF = (BN <= 64) ? 4 : 2;           // accumulator buffers (ring)
+    static constexpr int TMEM_P0 = NBUF * BN;                 // first column of the P operand ring
+    static constexpr int P_COLS = 2 * BK;                     // per stage: [hi 32 | lo 32]
+    static constexpr int TMEM_COLS = 512;                     // NBUF * BN + STAGES * P_COLS = 512
+    static_assert(NBUF * BN + STAGES * P_COLS <= 512, "tensor memory budget");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +107,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 // one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -106,6 +133,8 @@ __device__ __forceinline__ bool elect_one() {
 // round-to-nearest TF32 (10 explicit mantissa bits) with integer ops; the remainder x - hi is exact in FP32
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// lo part of the split whose hi part is the raw word (read truncated by the tensor core)
+__device__ __forceinline__ float tf32_lo(float x) { return tf32_hi(x - tf32_trunc(x)); }
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -119,7 +148,7 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
 }
 
 // barrier slots (8 B each)
-constexpr int NBUF = 4;                    // TMEM accumulator buffers (ring)
+constexpr int NBUF = 4;                    // max TMEM accumulator buffers (barrier slots)
 enum : int { B_FULL = 0, B_CONV = MAX_STAGES, B_EMPTY = 2 * MAX_STAGES, B_ACC_FULL = 3 * MAX_STAGES, B_ACC_EMPTY = 3 * MAX_STAGES + NBUF };
 
 // Persistent kernel: each CTA walks work items (p tile, q tile, k split) item = blockIdx.x + i*gridDim.x.
@@ -151,7 +180,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             mbar_init(BAR(B_CONV + s), NCONV / 32);        // one arrival per converter warp
             mbar_init(BAR(B_EMPTY + s), 1);
         }
-        for (int b = 0; b < NBUF; ++b) {
+        for (int b = 0; b < cfg::NBUF; ++b) {
             mbar_init(BAR(B_ACC_FULL + b), 1);
             mbar_init(BAR(B_ACC_EMPTY + b), NDRAIN / 32);  // one arrival per promotion warp
         }
@@ -195,7 +224,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     if (trace && blockIdx.x == 0 && lane == 0 && it + kb < 64) trace[(it + kb) * 4 + 0] = clock64();
                     mbar_arrive_expect_tx(BAR(B_FULL + s), BOX_ROWS * BK * 4);
                     if (lane < PB) tma_load_2d(st + lane * (BOX_ROWS * BK * 4), &tmP, (kb0 + kb) * BK, p0 + lane * BOX_ROWS, BAR(B_FULL + s));
-                    else tma_load_2d(st + 2 * cfg::P_TILE + (lane - PB) * (BOX_ROWS * BK * 4), &tmQ, (kb0 + kb) * BK, q0 + (lane - PB) * BOX_ROWS, BAR(B_FULL + s));
+                    else tma_load_2d(st + cfg::P_TILE + (lane - PB) * (BOX_ROWS * BK * 4), &tmQ, (kb0 + kb) * BK, q0 + (lane - PB) * BOX_ROWS, BAR(B_FULL + s));
                 }
                 __syncwarp();
             }
@@ -207,15 +236,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
-                const int cg = ch + kb / drain_kb, buf = cg % NBUF, use = cg / NBUF;
+                const int cg = ch + kb / drain_kb, buf = cg % cfg::NBUF, use = cg / cfg::NBUF;
                 const bool chunk_start = (kb % drain_kb) == 0;
                 if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
                 mbar_wait(BAR(B_CONV + s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_d + (uint32_t)(buf * BN);
                 const uint32_t st = base + s * cfg::STAGE;
-                const uint64_t p_hi = make_sdesc(st), p_lo = make_sdesc(st + cfg::P_TILE);
-                const uint64_t q_hi = make_sdesc(st + 2 * cfg::P_TILE), q_lo = make_sdesc(st + 2 * cfg::P_TILE + cfg::Q_TILE);
+                const uint32_t p_hi = tmem_d + (uint32_t)(cfg::TMEM_P0 + s * cfg::P_COLS), p_lo = p_hi + BK;
+                const uint64_t q_hi = make_sdesc(st + cfg::P_TILE), q_lo = make_sdesc(st + cfg::P_TILE + cfg::Q_TILE);
                 const bool last_of_chunk = (kb % drain_kb) == drain_kb - 1 || kb == nkb - 1;
                 if (elect_one()) {
                     if (trace && blockIdx.x == 0 && it + kb < 64) trace[(it + kb) * 4 + 2] = clock64();
@@ -224,11 +253,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 floats = 32 bytes along K inside the swizzle span
                         const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
                         if (mode == 1) {                                    // debug: plain TF32
-                            umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, first);
+                            umma_tf32_ts(acc, p_hi + 8 * k, q_hi + adv, idesc, first);
                         } else {
-                            umma_tf32(acc, p_lo + adv, q_hi + adv, idesc, first);
-                            umma_tf32(acc, p_hi + adv, q_lo + adv, idesc, 1u);
-                            umma_tf32(acc, p_hi + adv, q_hi + adv, idesc, 1u);
+                            umma_tf32_ts(acc, p_lo + 8 * k, q_hi + adv, idesc, first);
+                            umma_tf32_ts(acc, p_hi + 8 * k, q_lo + adv, idesc, 1u);
+                            umma_tf32_ts(acc, p_hi + 8 * k, q_hi + adv, idesc, 1u);
                         }
                     }
                     umma_commit(BAR(B_EMPTY + s));                          // frees the stage when the MMAs retire
@@ -240,45 +269,42 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         } else if (warp >= 2 && warp < 6) {
             // ------------------------------------------------------------ converters: x -> (tf32 hi, lo)
             const int ct = threadIdx.x - 64;
+            const int quad = warp & 3;                               // TMEM lane quadrant this warp may write
+            const int prow_t = quad * 32 + lane;                     // P tile row = TMEM lane
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 mbar_wait(BAR(B_FULL + s), ph);
                 if (trace && blockIdx.x == 0 && ct == 0 && it + kb < 64) trace[(it + kb) * 4 + 1] = clock64();
                 uint8_t* st = gbase + s * cfg::STAGE;
-                // all of this thread's 16-byte chunks are loaded first (independent LDS in flight), then split
-                // into TF32 hi (in place) and the exact FP32 remainder lo (second tile)
-                constexpr int NP = cfg::P_TILE / 16 / NCONV, NQ = cfg::Q_TILE / 16 / NCONV;
-                float4* p_hi = reinterpret_cast<float4*>(st) + ct;
-                float4* p_lo = reinterpret_cast<float4*>(st + cfg::P_TILE) + ct;
-                float4* q_hi = reinterpret_cast<float4*>(st + 2 * cfg::P_TILE) + ct;
-                float4* q_lo = reinterpret_cast<float4*>(st + 2 * cfg::P_TILE + cfg::Q_TILE) + ct;
-                float4 v[NP + NQ];
+                // P: this thread's row (8 x 16 bytes, un-swizzled while reading) -> tensor memory [hi 32 | lo 32]
+                {
+                    const float4* prow = reinterpret_cast<const float4*>(st + prow_t * (BK * 4));
+                    uint32_t r[BK];
 #pragma unroll
-                for (int i = 0; i < NP; ++i) v[i] = p_hi[i * NCONV];
-#pragma unroll
-                for (int i = 0; i < NQ; ++i) v[NP + i] = q_hi[i * NCONV];
-#pragma unroll
-                for (int i = 0; i < NP + NQ; ++i) {
-                    const float4 x = v[i];
-                    if (mode == 5) {
-                        // the MMA reads the raw FP32 word as TF32 (low 13 mantissa bits ignored = truncation), so hi needs
-                        // no write; lo = round-to-nearest-TF32 of the exact truncation remainder: |x - hi - lo| <= 2^-22 |x|
-                        const float4 l = make_float4(tf32_hi(x.x - tf32_trunc(x.x)), tf32_hi(x.y - tf32_trunc(x.y)),
-                                                     tf32_hi(x.z - tf32_trunc(x.z)), tf32_hi(x.w - tf32_trunc(x.w)));
-                        if (i < NP) p_lo[i * NCONV] = l; else q_lo[(i - NP) * NCONV] = l;
-                    } else if (mode == 4) {
-                        // experiment: the MMA reads the raw FP32 word as TF32 (low 13 mantissa bits ignored), so only
-                        // the truncation remainder has to be written
-                        const float4 l = make_float4(x.x - tf32_trunc(x.x), x.y - tf32_trunc(x.y), x.z - tf32_trunc(x.z), x.w - tf32_trunc(x.w));
-                        if (i < NP) p_lo[i * NCONV] = l; else q_lo[(i - NP) * NCONV] = l;
-                    } else {
-                        const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-                        const float4 l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-                        if (i < NP) { p_hi[i * NCONV] = h; p_lo[i * NCONV] = l; }
-                        else { q_hi[(i - NP) * NCONV] = h; q_lo[(i - NP) * NCONV] = l; }
+                    for (int c = 0; c < BK / 4; ++c) {
+                        const float4 x = prow[c ^ (prow_t & 7)];
+                        r[4 * c] = __float_as_uint(x.x); r[4 * c + 1] = __float_as_uint(x.y);
+                        r[4 * c + 2] = __float_as_uint(x.z); r[4 * c + 3] = __float_as_uint(x.w);
                     }
+                    const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cfg::TMEM_P0 + s * cfg::P_COLS);
+                    tmem_st32(ta, r);
+#pragma unroll
+                    for (int j = 0; j < BK; ++j) r[j] = __float_as_uint(tf32_lo(__uint_as_float(r[j])));
+                    tmem_st32(ta + BK, r);
                 }
+                // Q: lo tile only (the raw tile is the hi operand)
+                constexpr int NQ = cfg::Q_TILE / 16 / NCONV;
+                const float4* q_hi = reinterpret_cast<const float4*>(st + cfg::P_TILE) + ct;
+                float4* q_lo = reinterpret_cast<float4*>(st + cfg::P_TILE + cfg::Q_TILE) + ct;
+                float4 v[NQ];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) v[i] = q_hi[i * NCONV];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i)
+                    q_lo[i * NCONV] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
@@ -293,7 +319,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 #pragma unroll
             for (int j = 0; j < BN; ++j) accr[j] = 0.f;
             for (int chunk = 0; chunk < nchunks; ++chunk) {
-                const int cg = ch + chunk, buf = cg % NBUF, use = cg / NBUF;
+                const int cg = ch + chunk, buf = cg % cfg::NBUF, use = cg / cfg::NBUF;
                 mbar_wait(BAR(B_ACC_FULL + buf), use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
