@@ -7,10 +7,13 @@
 //     CTA `kr` of the cluster contracts the K-slice [kr*H/2, (kr+1)*H/2) of those rows against the same slice of
 //     h_{t-1} for all (<= 64) sequences, so per step a CTA streams 96 x H/2 weights (L2-resident: W_hh is read
 //     T times) and only 64 x H/2 of the hidden state.
-//   * operands: A = [h_hi ; h_lo] (64 + 64 rows), B = W_hi then W_lo (96 rows): two M128 N96 K8 MMAs per k-step
-//     give h_hi.W + h_lo.W in TMEM lanes 0-63 / 64-127 (all four split products).  The tensor core truncates
-//     when it adds into its FP32 accumulator, so every 64 k the partial sum is drained (tcgen05.ld) and added
-//     round-to-nearest into FP32 registers (same scheme as linear_tc.cu).
+//   * operands: A = [h_hi ; h_lo] (64 + 64 rows) lives in TENSOR MEMORY (written by tcgen05.st, read by TS-mode
+//     MMAs), B = W_hi then W_lo (96 rows) in shared memory: two M128 N96 K8 MMAs per k-step give h_hi.W + h_lo.W
+//     in TMEM lanes 0-63 / 64-127 (all four split products).  Split: hi = the raw FP32 word (the tensor core
+//     ignores the low 13 mantissa bits), lo = RN_tf32(x - trunc(x)), so only W_lo is ever written to shared
+//     memory - the shared-memory pipe (LDS/STS + UMMA operand reads), not the tensor pipe, bounds this kernel.
+//     The tensor core truncates when it adds into its FP32 accumulator, so every 64 k the partial sum is drained
+//     (tcgen05.ld) and added round-to-nearest into FP32 registers (same scheme as linear_tc.cu).
 //   * end of step: hi + lo rows are combined through shared memory, the two K-slice partials through
 //     distributed shared memory (mbarrier handshake, no cluster-wide barrier); each CTA then finalises 16 units
 //     x 64 sequences: gates, h_t, h_t + residual, with h_{t-1} kept in registers.
@@ -36,17 +39,18 @@ constexpr int UPC = UC * KG;                // hidden units per cluster
 constexpr int NB = 3 * UPC;                 // W_hh rows per CTA (UMMA N) = 96
 constexpr int SB = 64;                      // sequences (A rows: 64 hi + 64 lo = UMMA M 128)
 constexpr int BK = 32;                      // floats per k-block = one 128-byte swizzle span
-constexpr int STAGES = 4;
-constexpr int H_TILE = SB * BK * 4;         //  8 192 B raw h tile (becomes the hi half)
-constexpr int A_TILE = 2 * H_TILE;          // 16 384 B
+constexpr int STAGES = 5;
+constexpr int H_TILE = SB * BK * 4;         //  8 192 B raw h tile
 
 constexpr int G_TILE = UPC * BK * 4;        //  4 096 B: one gate's rows = one TMA box
 constexpr int W_TILE = NB * BK * 4;         // 12 288 B
-constexpr int STAGE = A_TILE + 2 * W_TILE;  // 40 960 B: [h hi | h lo | W hi | W lo]
+constexpr int STAGE = H_TILE + 2 * W_TILE;  // 32 768 B: [h raw | W raw = hi | W lo]
 constexpr int PLD = 100;                    // row stride (floats) of the partial-sum buffer: conflict-free float4 rows
 constexpr int P_FLOATS = SB * PLD;
-constexpr int NBUF = 4;                     // TMEM accumulator ring
-constexpr int TMEM_COLS = 512;              // 4 x 96 -> power of two
+constexpr int NBUF = 3;                     // TMEM accumulator ring (3 x 96 columns)
+constexpr int TMEM_A = NBUF * NB;           // A operand ring: STAGES x 32 columns, lanes 0-63 h_hi, 64-127 h_lo
+constexpr int TMEM_COLS = 512;
+static_assert(NBUF * NB + STAGES * BK <= 512, "tensor memory budget");
 constexpr int DRAIN_KB = 2;                 // k-blocks per promotion
 constexpr int NPROM = 256, NCONV = 256;
 constexpr int THREADS = 128 + NPROM + NCONV;
@@ -70,11 +74,6 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 split_store(float4 x, float4* lo) {
-    const float4 h = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-    *lo = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
-    return h;
-}
 
 // debug timestamps of CTA 0: trace[step*8 + i] (step < 32) and trace[256 + kb*8 + i] for the k-blocks of step 2
 #define GRU_TRACE_STEP(i) do { if (trace && blockIdx.x == 0 && step < 32) trace[step * 8 + (i)] = clock64(); } while (0)
@@ -144,7 +143,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (lane < 3) {
                     if (lane == 0) GRU_TRACE_KB(0);
                     mbar_arrive_expect_tx(BAR(B_FULL_W + s), G_TILE);
-                    tma_load_2d(base + s * STAGE + A_TILE + lane * G_TILE, &tmW, k0 + kb * BK, lane * H + u0, BAR(B_FULL_W + s));
+                    tma_load_2d(base + s * STAGE + H_TILE + lane * G_TILE, &tmW, k0 + kb * BK, lane * H + u0, BAR(B_FULL_W + s));
                 }
                 __syncwarp();
             }
@@ -202,15 +201,15 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 tc_fence_after();
                 const uint32_t acc = tmem_d + (uint32_t)(buf * NB);
                 const uint32_t st = base + s * STAGE;
-                const uint64_t a = make_sdesc_sw128(st);
-                const uint64_t b_hi = make_sdesc_sw128(st + A_TILE), b_lo = make_sdesc_sw128(st + A_TILE + W_TILE);
+                const uint32_t a = tmem_d + (uint32_t)(TMEM_A + s * BK);
+                const uint64_t b_hi = make_sdesc_sw128(st + H_TILE), b_lo = make_sdesc_sw128(st + H_TILE + W_TILE);
                 const bool last_of_chunk = (kb % DRAIN_KB) == DRAIN_KB - 1 || kb == NKB - 1;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                        umma_tf32(acc, a + adv, b_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
-                        umma_tf32(acc, a + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32_ts(acc, a + 8 * k, b_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                        umma_tf32_ts(acc, a + 8 * k, b_lo + adv, idesc, 1u);
                     }
                     umma_commit(BAR(B_EMPTY + s));
                     if (last_of_chunk) umma_commit(BAR(B_ACC_FULL + buf));
@@ -222,33 +221,48 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             ch += nchunks;
         }
     } else if (warp >= 12) {
-        // ------------------------------------------------------------ converters: x -> (tf32 hi in place, lo)
+        // ------------------------------------------------------------ converters
+        // W: lo tile only (the raw tile is the hi operand).  h: each thread moves half of one row from shared memory
+        // into tensor memory - lanes 0-63 get the raw words (hi), lanes 64-127 the lo parts.
         const int ct = threadIdx.x - (128 + NPROM);
+        const int quad = warp & 3, half = (warp - 12) >> 2;           // TMEM lane quadrant / which 16 of the 32 columns
+        const int arow = quad * 32 + lane, hseq = arow & 63;          // A row = TMEM lane; source sequence
         int it = 0;
         for (int step = first_gemm; step < T; ++step) {
             for (int kb = 0; kb < NKB; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 uint8_t* st = gbase + s * STAGE;
-                float4* w_hi = reinterpret_cast<float4*>(st + A_TILE) + ct;
-                float4* w_lo = reinterpret_cast<float4*>(st + A_TILE + W_TILE) + ct;
-                float4* h_hi = reinterpret_cast<float4*>(st) + ct;
-                float4* h_lo = reinterpret_cast<float4*>(st + H_TILE) + ct;
-                constexpr int NW = W_TILE / 16 / NCONV, NH = H_TILE / 16 / NCONV;   // 3, 2
+                const float4* w_hi = reinterpret_cast<const float4*>(st + H_TILE) + ct;
+                float4* w_lo = reinterpret_cast<float4*>(st + H_TILE + W_TILE) + ct;
+                constexpr int NW = W_TILE / 16 / NCONV;               // 3
                 mbar_wait(BAR(B_FULL_W + s), ph);
                 if (ct == 0) GRU_TRACE_KB(4);
                 float4 v[NW];
 #pragma unroll
                 for (int i = 0; i < NW; ++i) v[i] = w_hi[i * NCONV];
 #pragma unroll
-                for (int i = 0; i < NW; ++i) w_hi[i * NCONV] = split_store(v[i], &w_lo[i * NCONV]);
+                for (int i = 0; i < NW; ++i)
+                    w_lo[i * NCONV] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
                 mbar_wait(BAR(B_FULL_H + s), ph);
                 if (ct == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
-                float4 u[NH];
+                {
+                    const float4* hrow = reinterpret_cast<const float4*>(st + hseq * (BK * 4));
+                    uint32_t r[16];
 #pragma unroll
-                for (int i = 0; i < NH; ++i) u[i] = h_hi[i * NCONV];
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 x = hrow[(half * 4 + c) ^ (hseq & 7)];     // un-swizzle
+                        r[4 * c] = __float_as_uint(x.x); r[4 * c + 1] = __float_as_uint(x.y);
+                        r[4 * c + 2] = __float_as_uint(x.z); r[4 * c + 3] = __float_as_uint(x.w);
+                    }
+                    if (quad >= 2) {
 #pragma unroll
-                for (int i = 0; i < NH; ++i) h_hi[i * NCONV] = split_store(u[i], &h_lo[i * NCONV]);
+                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(tf32_lo(__uint_as_float(r[j])));
+                    }
+                    tmem_st16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TMEM_A + s * BK + half * 16), r);
+                }
+                tmem_st_wait();
+                tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
