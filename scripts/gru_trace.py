@@ -40,10 +40,10 @@ for s in range(T):
     prev = v[6]
 kb = t[256:].view(64, 8)
 k0 = int(kb[0, 0])
-print("step 2 k-blocks (cycles; + = relative to W issue): W_issue | h_issue+ convW_start+ convH_start+ conv_done+ mma_issued+ | period")
+print("step 2 k-blocks (cycles; + = relative to W issue): W_issue | h_issue+ convW_start+ convH_start+ conv_done(warp12)+ mma:acc_free+ mma:conv_seen+ mma_issued+ | period")
 prev = None
 for i in range(32):
     v = [int(x) - k0 for x in kb[i]]
     a = v[0]
-    print(f"{i:3d} {a:8d} | " + " ".join(f"{v[j] - a:8d}" for j in (1, 4, 5, 6, 7)) + f"   {'' if prev is None else a - prev}")
+    print(f"{i:3d} {a:8d} | " + " ".join(f"{v[j] - a:8d}" for j in (1, 4, 5, 6, 2, 3, 7)) + f"   {'' if prev is None else a - prev}")
     prev = a

@@ -197,7 +197,9 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 const int cg = ch + kb / DRAIN_KB, buf = cg % NBUF, use = cg / NBUF;
                 const bool chunk_start = (kb % DRAIN_KB) == 0;
                 if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
+                if (lane == 0) GRU_TRACE_KB(2);
                 mbar_wait(BAR(B_CONV + s), ph);
+                if (lane == 0) GRU_TRACE_KB(3);
                 tc_fence_after();
                 const uint32_t acc = tmem_d + (uint32_t)(buf * NB);
                 const uint32_t st = base + s * STAGE;
@@ -371,7 +373,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (hn && step == T - 1) *reinterpret_cast<float4*>(hn + (int64_t)seq * H + unit) = h;
             }
             if (step < T - 1) {
-                fence_proxy_async_global();
+                fence_proxy_async_global();            // generic-proxy stores of h_t -> async-proxy (TMA) reads by other CTAs
                 named_bar_sync(1, NPROM);
                 if (pt == 0) st_release_gpu(flags + blockIdx.x, (unsigned)(step + 1));
             }

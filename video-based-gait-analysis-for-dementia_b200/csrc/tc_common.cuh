@@ -35,9 +35,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: a waiting warp sleeps instead of taking issue slots
         if (!ok) guard.tick();
     } while (!ok);
 }
@@ -48,9 +48,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: a waiting warp sleeps instead of taking issue slots
         if (!ok) guard.tick();
     } while (!ok);
 }
