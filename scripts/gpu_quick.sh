@@ -7,7 +7,7 @@ echo "== tests ($KSEL)"; timeout 600 python -m pytest tests/test_gpu_parity.py -
 echo "== bench"; timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/${TAG}_bench.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('frames/s', round(d['value']), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'lbs GB/s', round(d['roofline']['achieved']), 'frac', round(d['roofline']['frac'],3))
+print('frames/s', round(d['value']), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'lbs GB/s', round(d['roofline']['achieved']), 'frac', round(d['roofline']['frac'],3), 'single-launch frac', round(d['roofline'].get('frac_single_launch_event_pair', 0),3))
 print({k:(v['ms'],v['launches']) for k,v in d['stages'].items()})"
 if [ -n "$NCU" ]; then
   echo "== ncu full $NCU"

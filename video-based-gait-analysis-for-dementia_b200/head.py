@@ -146,6 +146,29 @@ class GaitHead(nn.Module):
             res[name] = {"ms": tot / iters, "launches": (L.launch_count() - n0) // iters}
         return res
 
+    @torch.no_grad()
+    def time_stage_back_to_back(self, name: str, launches: int = 8, repeats: int = 5):
+        """Average duration (ms) of one launch of stage `name`, timed as `launches` consecutive launches between
+        ONE pair of CUDA events, alternating between the planned buffer slots (with two slots the LBS stage
+        touches 2 x 170 MB > the 126 MB L2, so no launch finds its operands cached).  A single launch bracketed
+        by its own event pair also pays ~5 us of event / launch gap, which is not kernel time."""
+        if len(self._slots) < 2:
+            raise L.GaitLibraryError("time_stage_back_to_back needs plan(..., slots=2)")
+        for p in self._slots:
+            self._launch(p)
+        fns = [dict(self._stages(p))[name] for p in self._slots]
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(repeats):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(launches):
+                fns[i % len(fns)]()
+            b.record()
+            b.synchronize()
+            best = min(best, a.elapsed_time(b) / launches)
+        return best
+
     def capture(self, S: int, T: int, slots: int = 1):
         """Plan buffers for (S,T) and capture one step per slot into a CUDA graph."""
         self.plan(S, T, slots)
