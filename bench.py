@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--variant", choices=["sparse", "dense"], default="sparse",
                     help="synthetic SMPL weights: SMPL-like sparse (<=4 skin weights / vertex) or fully dense")
+    ap.add_argument("--joints-only", action="store_true",
+                    help="BASELINE config 5: Kinect-25 joints without mesh write-back (the skinned mesh never leaves the SMs)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gather", choices=["none", "joints", "mesh"], default="none",
                     help="NCCL all-gather of Kinect-25 joints (or joints+mesh) inside the timed step (N>1)")
@@ -83,7 +85,7 @@ def make_models(args, want_gpu: bool, want_oracle: bool):
     head = oracle = None
     if want_gpu:
         from gaitb200.head import GaitHead
-        head = GaitHead(smpl_data, mean, reg_state, gru_state).cuda()
+        head = GaitHead(smpl_data, mean, reg_state, gru_state, write_mesh=not getattr(args, "joints_only", False)).cuda()
     if want_oracle:
         from oracle.head import GaitHeadOracle
         oracle = GaitHeadOracle(smpl_data, mean, reg_state, gru_state)
@@ -142,8 +144,11 @@ def run_reference(args, rank: int):
 
 
 def workload_config(args, world):
-    return {"workload": f"BASELINE configs[1]: {args.seqs_per_gpu} sequences x {args.frames} frames per GPU, "
-                        "GRU(2048) + 3-iter HMR regressor + SMPL LBS, full 6890-vertex mesh + Kinect-25 output",
+    jo = getattr(args, "joints_only", False)
+    return {"workload": (f"BASELINE configs[4] (joints-only): {args.seqs_per_gpu} sequences x {args.frames} frames per GPU, "
+                         "GRU(2048) + 3-iter HMR regressor + SMPL LBS, Kinect-25 output, no mesh write-back" if jo else
+                         f"BASELINE configs[1]: {args.seqs_per_gpu} sequences x {args.frames} frames per GPU, "
+                         "GRU(2048) + 3-iter HMR regressor + SMPL LBS, full 6890-vertex mesh + Kinect-25 output"),
             "seqs_per_gpu": args.seqs_per_gpu, "frames_per_seq": args.frames,
             "global_frames_per_step": args.seqs_per_gpu * args.frames * world, "smpl_weights": args.variant,
             "sharding": f"sequences x{world}, no data-path collective" + ("" if args.gather == "none" else f", final all-gather: {args.gather}"),
@@ -298,7 +303,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item()) / e2e_steps
     e2e_value = F * world / (e2e_ms / 1e3)
-    e2e_check = float((host_outs[(e2e_steps - 1) % 2]["verts"] - head.outputs((e2e_steps - 1) % 2)["verts"].cpu()).abs().max())
+    ck = "kinect25" if args.joints_only else "verts"
+    e2e_check = float((host_outs[(e2e_steps - 1) % 2][ck] - head.outputs((e2e_steps - 1) % 2)[ck].cpu()).abs().max())
 
     if rank != 0:
         return
@@ -307,13 +313,13 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # dominant HBM kernel: average launch duration over 8 consecutive launches between one event pair, alternating
     # two buffer sets (2 x 170 MB > L2); the single-launch figure (own event pair after an L2 flush) is kept beside it
     lbs_ms = head.time_stage_back_to_back("lbs", launches=8, repeats=5)
-    lbs_bytes = F * LBS_BYTES_PER_FRAME + LBS_BYTES_ONCE
+    lbs_bytes = F * (LBS_BYTES_PER_FRAME - (6890 * 3 * 4 - 21 * 12 if args.joints_only else 0)) + LBS_BYTES_ONCE
     lbs_gbs = lbs_bytes / (lbs_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tp = ROOT / "profiles" / "lbs_traffic.json"          # dram bytes per launch from the committed ncu --set full capture
     if tp.exists():
         td = json.loads(tp.read_text())
-        if int(td.get("frames", -1)) == F:
+        if int(td.get("frames", -1)) == F and not args.joints_only:
             traffic, traffic_src = td["dram_read_bytes"] + td["dram_write_bytes"], td.get("source")
     roofline = {"kernel": "smpl_lbs_tc_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
@@ -358,7 +364,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "roofline": roofline,
         "stages": stage_report,
         "cpu_baseline": cpu_baseline,
-        "whole_step_hbm_frac": (F * (IN_BYTES_PER_FRAME + OUT_BYTES_PER_FRAME) / (ms_per_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
+        "whole_step_hbm_frac": (F * (IN_BYTES_PER_FRAME + OUT_BYTES_PER_FRAME - (6890 * 12 if args.joints_only else 0))
+                                / (ms_per_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
         "wall_s_timed_region": t_wall,
         "step_ms_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
         "library": str(_lib.LIB_PATH.relative_to(ROOT)),

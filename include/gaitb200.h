@@ -162,6 +162,13 @@ int gait_smpl_lbs_pack(const float* lbs_weights, float* packed, int64_t V, gait_
 size_t gait_smpl_lbs_aop_bytes(int64_t F);
 int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
                      float* verts, float* jx_partial, int64_t F, int64_t V, gait_stream_t stream);
+/* Joints-only variant (BASELINE config 5, "no mesh write-back"): the same skinning, but the mesh is never written to
+ * HBM.  Only the n_lm landmark vertices lm_idx[] (int32 vertex ids; the VertexJointSelector landmarks the joint sets
+ * use) go to lm_out (F, n_lm, 3), plus the fused regressor-row partials; gait_joints_assemble then takes lm_out as its
+ * `verts` with V = n_lm and landmarks = 0..n_lm-1. */
+int gait_smpl_lbs_tc_joints(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                            float* jx_partial, const int32_t* lm_idx, int n_lm, float* lm_out, int64_t F, int64_t V,
+                            gait_stream_t stream);
 /* vertices2joints (smplx lbs; lib/models/smpl.py:113, pare.py:70-76, spin.py:279-282):
  * out (F,Rj,3) = Jreg (Rj,V) . verts (F,V,3). */
 int gait_joint_regress(const float* verts, const float* Jreg, float* out, int64_t F, int64_t V, int Rj,

@@ -434,6 +434,37 @@ def test_head_graph_replay_dense_variant(lib_loaded):
         _check_head(head.outputs(), oracle(feats))
 
 
+def test_head_joints_only_c5(lib_loaded):
+    """BASELINE config 5: the joints-only path (mesh never written to HBM) gives bit-identical joints, Kinect-25
+    joints, kp_2d and theta to the full-mesh path on the same inputs, and agrees with the oracle."""
+    from gaitb200.head import GaitHead
+    from oracle.head import GaitHeadOracle
+    data = synthetic.make_smpl_data(seed=0, variant="sparse")
+    mean = synthetic.make_mean_params()
+    rs = synthetic.make_regressor_state(seed=0, decoder_gain=0.3)
+    gs = synthetic.make_gru_state(seed=0)
+    full = GaitHead(data, mean, rs, gs).cuda()
+    lean = GaitHead(data, mean, rs, gs, write_mesh=False).cuda()
+    for S, T_ in [(3, 7), (8, 16)]:
+        feats = synthetic.make_features(S, T_, seed=77)
+        a = {k: v.clone() for k, v in full(feats.cuda()).items()}
+        b = {k: v.clone() for k, v in lean(feats.cuda()).items()}
+        assert "verts" not in b and lean._plan["verts"] is None
+        for k in ("kp_3d", "kinect25", "kp_2d", "theta", "rotmat"):
+            assert torch.equal(a[k], b[k]), k
+        ref = GaitHeadOracle(data, mean, rs, gs)(feats)
+        assert maxerr(b["kinect25"], ref["kinect25"]) <= TOL_V
+        assert maxerr(b["kp_2d"], ref["kp_2d"]) <= TOL_2D
+
+
+def test_head_long_clip_c4(lib_loaded):
+    """BASELINE config 4: one long gait clip (S = 1); the recurrence runs T-1 dependent steps in the persistent kernel."""
+    head, oracle, _ = _heads()
+    feats = synthetic.make_features(1, 300, seed=5)
+    out = head(feats.cuda())
+    _check_head(out, oracle(feats))
+
+
 def test_full_size_properties_c2(lib_loaded):
     """BASELINE config 2 (64 x 16 frames, full mesh): size-independent properties.
     (a) every rotation matrix is orthonormal with det +1; (b) Kinect-25 is the spin2 gather of

@@ -48,6 +48,7 @@ _SIGS = {
     "gait_smpl_lbs_pack": [P, P, I64, P],
     "gait_smpl_lbs_aop_bytes": [I64],
     "gait_smpl_lbs_tc": [P, I64, P, P, P, P, P, I64, I64, P],
+    "gait_smpl_lbs_tc_joints": [P, I64, P, P, P, P, P, I32, P, I64, I64, P],
     "gait_joint_regress": [P, P, P, I64, I64, I32, P],
     "gait_joints_assemble": [P, P, I64, P, I32, P, I32, I32, I64, P, I32, P, P, I64, F32, F32, F32, P, P, I32, P, I64, P],
     "gait_gather_joints": [P, I32, P, I32, P, I64, P],

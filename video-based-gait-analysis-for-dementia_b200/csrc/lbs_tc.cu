@@ -152,11 +152,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <bool HAS_JX>
+// MESH = false is the joints-only variant (BASELINE config 5): the skinned vertices never leave the SM; only the `n_lm`
+// landmark vertices lm_idx[] the joint sets need are written, to lm_out (F, n_lm, 3), next to the fused regressor row.
+template <bool HAS_JX, bool MESH>
 __global__ void __launch_bounds__(THREADS3, 1)
 smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restrict__ Aop,
                    const float* __restrict__ Wpack, const float* __restrict__ jx, float* __restrict__ verts,
-                   float* __restrict__ jx_partial, int F, int V, int groups, int n_items) {
+                   float* __restrict__ jx_partial, const int32_t* __restrict__ lm_idx, int n_lm,
+                   float* __restrict__ lm_out, int F, int V, int groups, int n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto FULL = [&](int s) { return bar0 + 8u * s; };               // TMA landed (tx count)
@@ -360,12 +363,23 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                             o[0] = a; o[1] = bb; o[2] = c;
                         }
                     }
-                    // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 % 8 == 0)
-                    float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
-                    const float2* src = reinterpret_cast<const float2*>(row);
+                    if (MESH) {
+                        // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 % 8 == 0)
+                        float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
+                        const float2* src = reinterpret_cast<const float2*>(row);
 #pragma unroll
-                    for (int i = 0; i < 6; ++i)
-                        if (lane + 32 * i < n2) dst[lane + 32 * i] = src[lane + 32 * i];
+                        for (int i = 0; i < 6; ++i)
+                            if (lane + 32 * i < n2) dst[lane + 32 * i] = src[lane + 32 * i];
+                    } else {
+                        // landmark vertices of this tile only
+                        for (int l = lane; l < n_lm; l += 32) {
+                            const int lv = lm_idx[l] - v0;
+                            if (lv >= 0 && lv < nv) {
+                                float* o = lm_out + ((int64_t)(f0 + f) * n_lm + l) * 3;
+                                o[0] = row[lv * 3]; o[1] = row[lv * 3 + 1]; o[2] = row[lv * 3 + 2];
+                            }
+                        }
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic accesses precede the stage's TMA refill
@@ -407,13 +421,16 @@ size_t gait_smpl_lbs_aop_bytes(int64_t F) {
     return F <= 0 ? 0 : (size_t)ceil_div(F, lbs::FT) * lbs::A_BLOB;
 }
 
-int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
-                     float* verts, float* jx_partial, int64_t F, int64_t V, gait_stream_t stream) {
+static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                         float* verts, float* jx_partial, const int32_t* lm_idx, int n_lm, float* lm_out, int64_t F,
+                         int64_t V, cudaStream_t stream) {
     GAIT_REQUIRE(F >= 0 && V >= 0, "smpl_lbs_tc: negative size");
     if (F == 0 || V == 0) return GAIT_OK;
-    GAIT_REQUIRE(v_posed && Aop && Wpack && verts, "smpl_lbs_tc: null pointer");
+    const bool mesh = verts != nullptr;
+    GAIT_REQUIRE(v_posed && Aop && Wpack, "smpl_lbs_tc: null pointer");
+    GAIT_REQUIRE(mesh || (lm_out && lm_idx && n_lm > 0), "smpl_lbs_tc: neither a mesh nor a landmark output given");
     GAIT_REQUIRE((jx == nullptr) == (jx_partial == nullptr), "smpl_lbs_tc: jx and jx_partial go together");
-    GAIT_REQUIRE((V & 1) == 0 && aligned8(verts), "smpl_lbs_tc: V must be even and verts 8-byte aligned");
+    GAIT_REQUIRE((V & 1) == 0 && (!mesh || aligned8(verts)), "smpl_lbs_tc: V must be even and verts 8-byte aligned");
     const int64_t tiles = ceil_div(V, lbs::VT);
     GAIT_REQUIRE(ldv >= tiles * lbs::VT * 3 && (ldv & 3) == 0 && aligned16(v_posed) && F < (1ll << 31),
                  "smpl_lbs_tc: v_posed rows must be padded to 384*ceil(V/128) floats (ldv %% 4 == 0, 16-byte aligned)");
@@ -422,8 +439,10 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
     static bool attr = false;
     static int n_sms = 0;
     if (!attr) {
-        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
-        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
+        GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
         int dev = 0;
         GAIT_CUDA(cudaGetDevice(&dev));
         GAIT_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -436,13 +455,28 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
     CUtensorMap tmV;
     GAIT_TRY(make_tensor_map_2d(&tmV, 8, v_posed, (uint64_t)(tiles * lbs::VT * 3 / 2), (uint64_t)F, (uint64_t)ldv * sizeof(float),
                                 lbs::VT * 3 / 2, lbs::FT, false));
-    if (jx)
-        lbs::smpl_lbs_tc_kernel<true><<<grid, lbs::THREADS3, lbs::SMEM3, as_stream(stream)>>>(
-            tmV, Aop, Wpack, jx, verts, jx_partial, (int)F, (int)V, (int)groups, (int)n_items);
-    else
-        lbs::smpl_lbs_tc_kernel<false><<<grid, lbs::THREADS3, lbs::SMEM3, as_stream(stream)>>>(
-            tmV, Aop, Wpack, nullptr, verts, nullptr, (int)F, (int)V, (int)groups, (int)n_items);
+#define GAIT_LBS_LAUNCH(JX, MESH)                                                                                       \
+    lbs::smpl_lbs_tc_kernel<JX, MESH><<<grid, lbs::THREADS3, lbs::SMEM3, stream>>>(                                       \
+        tmV, Aop, Wpack, jx, verts, jx_partial, lm_idx, n_lm, lm_out, (int)F, (int)V, (int)groups, (int)n_items)
+    if (jx && mesh) GAIT_LBS_LAUNCH(true, true);
+    else if (jx) GAIT_LBS_LAUNCH(true, false);
+    else if (mesh) GAIT_LBS_LAUNCH(false, true);
+    else GAIT_LBS_LAUNCH(false, false);
+#undef GAIT_LBS_LAUNCH
     return check_launch("smpl_lbs_tc");
+}
+
+int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                     float* verts, float* jx_partial, int64_t F, int64_t V, gait_stream_t stream) {
+    GAIT_REQUIRE(verts != nullptr || (F == 0 || V == 0), "smpl_lbs_tc: null pointer");
+    return lbs_tc_launch(v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, nullptr, 0, nullptr, F, V, as_stream(stream));
+}
+
+int gait_smpl_lbs_tc_joints(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                            float* jx_partial, const int32_t* lm_idx, int n_lm, float* lm_out, int64_t F, int64_t V,
+                            gait_stream_t stream) {
+    GAIT_REQUIRE(n_lm > 0 && n_lm <= 1024, "smpl_lbs_tc_joints: 1..1024 landmark vertices");
+    return lbs_tc_launch(v_posed, ldv, Aop, Wpack, jx, nullptr, jx_partial, lm_idx, n_lm, lm_out, F, V, as_stream(stream));
 }
 
 }  // extern "C"

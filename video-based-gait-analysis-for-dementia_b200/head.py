@@ -61,7 +61,11 @@ class GaitHead(nn.Module):
             "ws": e(max(gru_bytes, hmr_bytes, 4) // 4), "gru_bytes": gru_bytes, "hmr_bytes": hmr_bytes,
             "state": e(F, _STATE_LD), "rotmat": e(F, 24, 3, 3), "Jp": e(F, 24, 3),
             "aop": e(lib.gait_smpl_lbs_aop_bytes(F) // 4),
-            "coef": e(F, 224), "v_posed": e(F, 384 * ((V + 127) // 128)), "verts": e(F, V, 3),
+            "coef": e(F, 224), "v_posed": e(F, 384 * ((V + 127) // 128)),
+            # full mesh (F,V,3), or in joints-only mode just the landmark vertices the joint sets read (config 5)
+            "verts": e(F, V, 3) if self.write_mesh else None,
+            "lm_verts": None if self.write_mesh else e(F, self.regressor.smpl._prepare()["n_landmarks"], 3),
+            "lm_iota": None if self.write_mesh else torch.arange(self.regressor.smpl._prepare()["n_landmarks"], dtype=torch.int32, device=dev),
             "extra": e((V + 127) // 128, F, 1, 3),
             "joints": e(F, 29, 3), "kp2d": e(F, 29, 2), "kinect": e(F, 25, 3), "theta": e(F, 85),
             "gather": torch.tensor(SPIN2_TO_KINECTV2, dtype=torch.int32, device=dev),
@@ -105,14 +109,21 @@ class GaitHead(nn.Module):
                 ptr(sk["J_shapedirs"]), ptr(sk["parents"]), None, ptr(p["Jp"]), ptr(p["coef"]), ptr(p["aop"]), F, st())),
             ("blend", lambda: call(
                 "gait_smpl_blend", ptr(p["coef"]), ptr(sk["basis_t"]), ptr(p["v_posed"]), sk["ldv"], F, 3 * V, st())),
-            ("lbs", lambda: call(
+            ("lbs", (lambda: call(
                 "gait_smpl_lbs_tc", ptr(p["v_posed"]), sk["ldv"], ptr(p["aop"]), ptr(sk["lbs_wpack"]),
-                ptr(sk["extra_thorax"]), ptr(p["verts"]), ptr(p["extra"]), F, V, st())),
-            ("joints", lambda: call(
+                ptr(sk["extra_thorax"]), ptr(p["verts"]), ptr(p["extra"]), F, V, st())) if self.write_mesh else (lambda: call(
+                "gait_smpl_lbs_tc_joints", ptr(p["v_posed"]), sk["ldv"], ptr(p["aop"]), ptr(sk["lbs_wpack"]),
+                ptr(sk["extra_thorax"]), ptr(p["extra"]), ptr(sk["landmarks"]), sk["n_landmarks"], ptr(p["lm_verts"]),
+                F, V, st()))),
+            ("joints", (lambda: call(
                 "gait_joints_assemble", ptr(p["Jp"]), ptr(p["verts"]), V, ptr(sk["landmarks"]), sk["n_landmarks"],
                 ptr(p["extra"]), 1, sk["vtiles"], F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
                 5000., 224., 112.,
-                ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st())),
+                ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st())) if self.write_mesh else (lambda: call(
+                "gait_joints_assemble", ptr(p["Jp"]), ptr(p["lm_verts"]), sk["n_landmarks"], ptr(p["lm_iota"]), sk["n_landmarks"],
+                ptr(p["extra"]), 1, sk["vtiles"], F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
+                5000., 224., 112.,
+                ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st()))),
             ("theta", lambda: call(
                 "gait_pack_theta", ptr(p["rotmat"]), cam, _STATE_LD, betas, _STATE_LD, ptr(p["theta"]), F, st())),
         ]
