@@ -196,6 +196,20 @@ int gait_gather_joints(const float* src, int Js, const int32_t* idx, int Jd, flo
 int gait_pack_theta(const float* R, const float* cam, int64_t ldcam, const float* betas, int64_t ldb,
                     float* theta, int64_t F, gait_stream_t stream);
 
+/* ---- post-processing next to the head ------------------------------ */
+/* One-Euro filter (lib/utils/one_euro_filter.py:5-46) over T frames of C channels, as lib/utils/smooth_pose.py:51-56,
+ * 84-88 drives it: x (T,C) sampled at t = 0,1,2,...; x_hat[0] = x[0], dx_0 = 0.  numpy float32 arithmetic, bit-exact. */
+int gait_one_euro_filter(const float* x, float* x_hat, int64_t T, int64_t C, double min_cutoff, double beta, double d_cutoff,
+                         gait_stream_t stream);
+/* convert_crop_cam_to_orig_img (lib/utils/demo_utils.py:176-193): cam (N,3) float32 [s,tx,ty] of the crop, bbox (N, ldb>=3)
+ * [cx, cy, h, ..] float32 or float64 -> out (N,4) [sx, sy, tx, ty] in bbox's dtype (numpy promotion). */
+int gait_crop_cam_to_orig_img(const float* cam, const void* bbox, int bbox_is_f64, int64_t ldb, double img_width,
+                              double img_height, void* out, int64_t N, gait_stream_t stream);
+/* convert_crop_coords_to_orig_img (lib/utils/demo_utils.py:196-209): keypoints (N,J,D>=2) float32 in [-1,1] crop units ->
+ * out (N,J,D) float32 original-image pixels (may alias keypoints). */
+int gait_crop_coords_to_orig_img(const void* bbox, int bbox_is_f64, int64_t ldb, const float* keypoints, float* out, int64_t N,
+                                 int J, int D, double crop_size, gait_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

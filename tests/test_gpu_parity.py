@@ -493,3 +493,53 @@ def test_full_size_properties_c2(lib_loaded):
     ref = oracle(feats[:1])
     sl = {k: v[:1] for k, v in out.items()}
     _check_head(sl, ref)
+
+
+# ------------------------------------------------------------------------------- post-processing
+def test_postproc_vs_reference_golden(golden, smpl_data, lib_loaded):
+    """One-Euro filter, crop->image conversions and smooth_pose against outputs of the reference's own
+    one_euro_filter.py / demo_utils.py / smooth_pose.py (tests/golden/make_golden_post.py).  Bit-exact where the
+    reference is numpy arithmetic; vertices / joints within the SMPL tolerance."""
+    from gaitb200 import postproc as PP
+    from gaitb200.smpl import SMPL
+    g = golden("postproc")
+    for tag in ("default", "stiff", "fast"):
+        mc, beta = g[f"oef_{tag}_params"]
+        out = PP.one_euro_filter(g["oef_in"], min_cutoff=mc, beta=beta)
+        assert out.dtype == np.float32 and np.array_equal(out, g[f"oef_{tag}"]), tag
+    o = PP.convert_crop_cam_to_orig_img(g["cc_cam"], g["cc_bbox"], 1280, 720)
+    assert o.dtype == np.float64 and np.array_equal(o, g["crop_cam_1280x720"])
+    o = PP.convert_crop_cam_to_orig_img(g["cc_cam"], g["cc_bbox"].astype(np.float32), 640, 480)
+    assert o.dtype == np.float32 and np.array_equal(o, g["crop_cam_f32"])
+    assert np.array_equal(PP.convert_crop_coords_to_orig_img(g["cc_bbox"], g["cc_kp"].copy(), 224), g["crop_coords_224"])
+    assert np.array_equal(PP.convert_crop_coords_to_orig_img(g["cc_bbox"].astype(np.float32), g["cc_kp"].copy(), 224),
+                          g["crop_coords_f32"])
+    smpl = SMPL(smpl_data).cuda()
+    for tag, kin in (("spin", False), ("kin", True)):
+        v, p, j = PP.smooth_pose(g["sp_aa"].copy(), g["sp_betas"], min_cutoff=0.004, beta=0.7, kinectv2=kin, smpl=smpl)
+        assert v.shape == (12, 6890, 3) and np.array_equal(p, g[f"sp_{tag}_pose"])
+        assert j.shape == g[f"sp_{tag}_joints"].shape and j.dtype == g[f"sp_{tag}_joints"].dtype
+        assert np.abs(v[:, ::53] - g[f"sp_{tag}_verts"]).max() <= TOL_V
+        assert np.abs(j - g[f"sp_{tag}_joints"]).max() <= TOL_V
+    v, p, j = PP.smooth_pose(g["sp_quat"].copy(), g["sp_betas"], min_cutoff=0.01, beta=0.5, kinectv2=True, smpl=smpl)
+    assert np.array_equal(p, g["sp_quat_pose"])
+    assert np.abs(v[:, ::53] - g["sp_quat_verts"]).max() <= TOL_V and np.abs(j - g["sp_quat_joints"]).max() <= TOL_V
+    with pytest.raises(ValueError):
+        PP.smooth_pose(np.zeros((4, 70), np.float32), np.zeros((4, 10), np.float32), smpl=smpl)
+
+
+def test_postproc_vs_oracle_long_and_empty(lib_loaded):
+    """A 900-frame clip (C4 length) through the filter against the numpy oracle, bit-exact; empty inputs."""
+    from gaitb200 import postproc as PP
+    from oracle import postproc as OP
+    rng = np.random.default_rng(3)
+    x = np.cumsum(rng.standard_normal((900, 24, 4)).astype(np.float32) * 0.03, axis=0).astype(np.float32)
+    assert np.array_equal(PP.one_euro_filter(x, min_cutoff=0.004, beta=0.7), OP.one_euro_filter(x, min_cutoff=0.004, beta=0.7))
+    assert PP.one_euro_filter(np.zeros((0, 72), np.float32)).shape == (0, 72)
+    assert PP.convert_crop_cam_to_orig_img(np.zeros((0, 3), np.float32), np.zeros((0, 4)), 10, 10).shape == (0, 4)
+    N = 1000
+    cam = rng.random((N, 3)).astype(np.float32) + 0.3
+    bbox = np.abs(rng.standard_normal((N, 4))) * 100 + 50
+    kp = (rng.random((N, 25, 2)) * 2 - 1).astype(np.float32)
+    assert np.array_equal(PP.convert_crop_cam_to_orig_img(cam, bbox, 1920, 1080), OP.convert_crop_cam_to_orig_img(cam, bbox, 1920, 1080))
+    assert np.array_equal(PP.convert_crop_coords_to_orig_img(bbox, kp.copy(), 224), OP.convert_crop_coords_to_orig_img(bbox, kp.copy(), 224))

@@ -124,3 +124,21 @@ def test_regressor_matches_reference(golden, smpl_data):
         o = reg(x, J_regressor=T(smpl_data["J_regressor_h36m"]))[-1]
         close(o["kp_3d"], g["reg_h36m_kp_3d"], 2e-6)
         close(o["kp_2d"], g["reg_h36m_kp_2d"], 1e-5)
+
+
+def test_postproc_oracle_vs_reference_golden(golden, smpl_data):
+    """oracle/postproc.py against the reference's own one_euro_filter.py / demo_utils.py / smooth_pose.py outputs."""
+    from oracle import postproc as P
+    g = golden("postproc")
+    for tag in ("default", "stiff", "fast"):
+        mc, b = g[f"oef_{tag}_params"]
+        assert np.array_equal(P.one_euro_filter(g["oef_in"], min_cutoff=mc, beta=b), g[f"oef_{tag}"])
+    assert np.array_equal(P.convert_crop_cam_to_orig_img(g["cc_cam"], g["cc_bbox"], 1280, 720), g["crop_cam_1280x720"])
+    assert np.array_equal(P.convert_crop_cam_to_orig_img(g["cc_cam"], g["cc_bbox"].astype(np.float32), 640, 480), g["crop_cam_f32"])
+    assert np.array_equal(P.convert_crop_coords_to_orig_img(g["cc_bbox"], g["cc_kp"].copy(), 224), g["crop_coords_224"])
+    for tag, kin in (("spin", False), ("kin", True)):
+        v, p, j = P.smooth_pose(smpl_data, g["sp_aa"].copy(), g["sp_betas"], kinectv2=kin)
+        assert np.array_equal(p, g[f"sp_{tag}_pose"]) and j.dtype == g[f"sp_{tag}_joints"].dtype
+        assert np.abs(v[:, ::53] - g[f"sp_{tag}_verts"]).max() <= 1e-6 and np.abs(j - g[f"sp_{tag}_joints"]).max() <= 1e-6
+    v, p, j = P.smooth_pose(smpl_data, g["sp_quat"].copy(), g["sp_betas"], min_cutoff=0.01, beta=0.5, kinectv2=True)
+    assert np.array_equal(p, g["sp_quat_pose"]) and np.abs(j - g["sp_quat_joints"]).max() <= 1e-6

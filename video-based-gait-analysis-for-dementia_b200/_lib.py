@@ -15,7 +15,7 @@ import torch
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("GAITB200_LIB", _HERE / "lib" / "libgaitb200.so"))
 
-P, I32, I64, F32, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+P, I32, I64, F32, F64, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGS = {
@@ -52,6 +52,9 @@ _SIGS = {
     "gait_joint_regress": [P, P, P, I64, I64, I32, P],
     "gait_joints_assemble": [P, P, I64, P, I32, P, I32, I32, I64, P, I32, P, P, I64, F32, F32, F32, P, P, I32, P, I64, P],
     "gait_gather_joints": [P, I32, P, I32, P, I64, P],
+    "gait_one_euro_filter": [P, P, I64, I64, F64, F64, F64, P],
+    "gait_crop_cam_to_orig_img": [P, P, I32, I64, F64, F64, P, I64, P],
+    "gait_crop_coords_to_orig_img": [P, I32, I64, P, P, I64, I32, I32, F64, P],
     "gait_pack_theta": [P, P, I64, P, I64, P, I64, P],
 }
 _RESTYPES = {
