@@ -14,7 +14,7 @@ x = torch.randn(S, T, H, device="cuda") * 0.5
 y = torch.empty(S, T, H, device="cuda"); out = torch.empty_like(y)
 nbytes = L.load().gait_gru_workspace_bytes(S, T, H)
 ws = torch.empty(nbytes // 4 + 1, device="cuda")
-tr = torch.zeros(768, dtype=torch.int64, device="cuda")
+tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
 w = {k: v.detach() for k, v in gru.named_parameters()}
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for rep in range(4):
@@ -38,7 +38,7 @@ for s in range(T):
     per = "" if prev is None else v[6] - prev
     print(f"{s:3d} " + " ".join(f"{a:9d}" for a in v) + f"   {per}")
     prev = v[6]
-kb = t[256:].view(64, 8)
+kb = t[256:768].view(64, 8)
 k0 = int(kb[0, 0])
 print("step 2 k-blocks (cycles; + = relative to W issue): W_issue | h_issue+ convW_start+ convH_start+ conv_done(warp12)+ mma:acc_free+ mma:conv_seen+ mma_issued+ | period")
 prev = None
@@ -47,3 +47,9 @@ for i in range(32):
     a = v[0]
     print(f"{i:3d} {a:8d} | " + " ".join(f"{v[j] - a:8d}" for j in (1, 4, 5, 6, 2, 3, 7)) + f"   {'' if prev is None else a - prev}")
     prev = a
+
+cv = t[768:768 + 64].view(8, 8)
+c0 = int(cv[:, 0].min())
+print("converter warps at step 2, k-block 10 (cycles from the first warp's start): start  W_landed  W_done  h_landed  st_issued  st_done  arrived")
+for w in range(8):
+    print(f"warp {12 + w}: " + " ".join(f"{int(cv[w, i]) - c0:8d}" for i in range(7)))

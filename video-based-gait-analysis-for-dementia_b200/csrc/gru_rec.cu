@@ -77,6 +77,7 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float
 
 // debug timestamps of CTA 0: trace[step*8 + i] (step < 32) and trace[256 + kb*8 + i] for the k-blocks of step 2
 #define GRU_TRACE_STEP(i) do { if (trace && blockIdx.x == 0 && step < 32) trace[step * 8 + (i)] = clock64(); } while (0)
+#define GRU_TRACE_CONV(i) do { if (trace && blockIdx.x == 0 && step == 2 && kb == 10 && lane == 0) trace[768 + (warp - 12) * 8 + (i)] = clock64(); } while (0)
 #define GRU_TRACE_KB(i) do { if (trace && blockIdx.x == 0 && step == 2 && kb < 64) trace[256 + kb * 8 + (i)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -189,38 +190,50 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
         constexpr uint32_t idesc = umma_idesc_tf32(128, NB);
-        int it = 0, ch = 0;
-        for (int step = first_gemm; step < T; ++step) {
-            for (int kb = 0; kb < NKB; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const int cg = ch + kb / DRAIN_KB, buf = cg % NBUF, use = cg / NBUF;
-                const bool chunk_start = (kb % DRAIN_KB) == 0;
-                if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
-                if (lane == 0) GRU_TRACE_KB(2);
-                mbar_wait(BAR(B_CONV + s), ph);
-                if (lane == 0) GRU_TRACE_KB(3);
-                tc_fence_after();
-                const uint32_t acc = tmem_d + (uint32_t)(buf * NB);
-                const uint32_t st = base + s * STAGE;
-                const uint32_t a = tmem_d + (uint32_t)(TMEM_A + s * BK);
-                const uint64_t b_hi = make_sdesc_sw128(st + H_TILE), b_lo = make_sdesc_sw128(st + H_TILE + W_TILE);
-                const bool last_of_chunk = (kb % DRAIN_KB) == DRAIN_KB - 1 || kb == NKB - 1;
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                        umma_tf32_ts(acc, a + 8 * k, b_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
-                        umma_tf32_ts(acc, a + 8 * k, b_lo + adv, idesc, 1u);
-                    }
-                    umma_commit(BAR(B_EMPTY + s));
-                    if (last_of_chunk) umma_commit(BAR(B_ACC_FULL + buf));
-                    GRU_TRACE_KB(7);
-                    if (kb == NKB - 1) GRU_TRACE_STEP(2);
-                }
-                __syncwarp();
+        // The barrier probes of k-block i+1 are issued BEFORE the MMAs of k-block i and consumed after them: a probe's
+        // shared-memory round trip (hundreds of cycles under converter traffic) then overlaps the MMA issue instead of
+        // serialising with it.  Ring positions are kept as wrapping counters (no div/mod in the loop).
+        const int total = (T - first_gemm) * NKB;
+        int s = 0, ph = 0;                                 // stage / phase of k-block `it`
+        int buf = 0, round = 0;                            // accumulator buffer, and how often every buffer was filled before
+        int kb = 0;
+        bool conv_ok = false, acc_ok = true;
+        if (total > 0) conv_ok = mbar_test(BAR(B_CONV + 0), 0);
+        for (int it = 0; it < total; ++it) {
+            const bool chunk_start = (kb % DRAIN_KB) == 0;
+            const bool last_of_chunk = (kb % DRAIN_KB) == DRAIN_KB - 1 || kb == NKB - 1;
+            if (chunk_start && round >= 1 && !acc_ok) mbar_wait(BAR(B_ACC_EMPTY + buf), (round - 1) & 1);
+            if (!conv_ok) mbar_wait(BAR(B_CONV + s), ph);
+            tc_fence_after();
+            // probes for the next k-block
+            const int s1 = (s + 1 == STAGES) ? 0 : s + 1, ph1 = (s + 1 == STAGES) ? ph ^ 1 : ph;
+            int buf1 = buf, round1 = round;
+            if (last_of_chunk && ++buf1 == NBUF) { buf1 = 0; ++round1; }
+            bool conv1 = false, acc1 = true;
+            if (it + 1 < total) {
+                conv1 = mbar_test(BAR(B_CONV + s1), ph1);
+                if (last_of_chunk && round1 >= 1) acc1 = mbar_test(BAR(B_ACC_EMPTY + buf1), (round1 - 1) & 1);
             }
-            ch += nchunks;
+            const uint32_t acc = tmem_d + (uint32_t)(buf * NB);
+            const uint32_t st = base + s * STAGE;
+            const uint32_t a = tmem_d + (uint32_t)(TMEM_A + s * BK);
+            const uint64_t b_hi = make_sdesc_sw128(st + H_TILE), b_lo = make_sdesc_sw128(st + H_TILE + W_TILE);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    umma_tf32_ts(acc, a + 8 * k, b_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                    umma_tf32_ts(acc, a + 8 * k, b_lo + adv, idesc, 1u);
+                }
+                umma_commit(BAR(B_EMPTY + s));
+                if (last_of_chunk) umma_commit(BAR(B_ACC_FULL + buf));
+                if (trace && blockIdx.x == 0 && it / NKB == 2 - first_gemm) trace[256 + kb * 8 + 7] = clock64();
+                if (trace && blockIdx.x == 0 && kb == NKB - 1 && it / NKB + first_gemm < 32) trace[(it / NKB + first_gemm) * 8 + 2] = clock64();
+            }
+            __syncwarp();
+            s = s1; ph = ph1; conv_ok = conv1;
+            if (last_of_chunk) { buf = buf1; round = round1; acc_ok = acc1; }
+            kb = (kb + 1 == NKB) ? 0 : kb + 1;
         }
     } else if (warp >= 12) {
         // ------------------------------------------------------------ converters
@@ -238,7 +251,9 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 const float4* w_hi = reinterpret_cast<const float4*>(st + H_TILE) + ct;
                 float4* w_lo = reinterpret_cast<float4*>(st + H_TILE + W_TILE) + ct;
                 constexpr int NW = W_TILE / 16 / NCONV;               // 3
+                GRU_TRACE_CONV(0);
                 mbar_wait(BAR(B_FULL_W + s), ph);
+                GRU_TRACE_CONV(1);
                 if (ct == 0) GRU_TRACE_KB(4);
                 float4 v[NW];
 #pragma unroll
@@ -246,7 +261,9 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
 #pragma unroll
                 for (int i = 0; i < NW; ++i)
                     w_lo[i * NCONV] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+                GRU_TRACE_CONV(2);
                 mbar_wait(BAR(B_FULL_H + s), ph);
+                GRU_TRACE_CONV(3);
                 if (ct == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
                 {
                     const float4* hrow = reinterpret_cast<const float4*>(st + hseq * (BK * 4));
@@ -263,11 +280,14 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                     }
                     tmem_st16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TMEM_A + s * BK + half * 16), r);
                 }
+                GRU_TRACE_CONV(4);
                 tmem_st_wait();
+                GRU_TRACE_CONV(5);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
+                GRU_TRACE_CONV(6);
                 if (ct == 0) GRU_TRACE_KB(6);
             }
         }

@@ -41,6 +41,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!ok) guard.tick();
     } while (!ok);
 }
+// Non-blocking probe: issue early, consume the result later (the smem round trip of a barrier probe is several hundred
+// cycles when the LSU/MIO queue is busy with converter traffic); fall back to mbar_wait() when it returns false.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 // same, acquiring at cluster scope (pairs with a remote mbar_arrive_remote_release)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
