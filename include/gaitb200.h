@@ -110,7 +110,7 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
                    int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T, int64_t I,
                    int64_t H, int reverse, void* workspace, size_t workspace_bytes, gait_stream_t stream);
 
-/* Debug hook: device buffer of 1024 uint64 receiving clock64 stamps of CTA 0 of the persistent recurrent kernel
+/* Debug hook: device buffer of 1280 uint64 receiving clock64 stamps of CTA 0 of the persistent recurrent kernel
  * (per step: [step*8+i]; per k-block of step 2: [256+kb*8+i]); NULL disables. */
 int gait_debug_gru_trace(unsigned long long* device_buffer);
 

@@ -14,7 +14,7 @@ x = torch.randn(S, T, H, device="cuda") * 0.5
 y = torch.empty(S, T, H, device="cuda"); out = torch.empty_like(y)
 nbytes = L.load().gait_gru_workspace_bytes(S, T, H)
 ws = torch.empty(nbytes // 4 + 1, device="cuda")
-tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
+tr = torch.zeros(1280, dtype=torch.int64, device="cuda")
 w = {k: v.detach() for k, v in gru.named_parameters()}
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for rep in range(4):
@@ -48,8 +48,10 @@ for i in range(32):
     print(f"{i:3d} {a:8d} | " + " ".join(f"{v[j] - a:8d}" for j in (1, 4, 5, 6, 2, 3, 7)) + f"   {'' if prev is None else a - prev}")
     prev = a
 
-cv = t[768:768 + 64].view(8, 8)
-c0 = int(cv[:, 0].min())
-print("converter warps at step 2, k-block 10 (cycles from the first warp's start): start  W_landed  W_done  h_landed  st_issued  st_done  arrived")
-for w in range(8):
-    print(f"warp {12 + w}: " + " ".join(f"{int(cv[w, i]) - c0:8d}" for i in range(7)))
+sk = t[1024:1280].view(128, 2)
+st0 = int(sk[:, 0].min())
+stored = sorted(int(x) - st0 for x in sk[:, 0])
+passed = sorted(int(x) - st0 for x in sk[:, 1])
+print("all CTAs, globaltimer ns from the first CTA's store of h_3: stored min/median/max", stored[0], stored[64], stored[-1],
+      "| flags of step 4 passed min/median/max", passed[0], passed[64], passed[-1])
+print("stored per CTA (ns):", [int(x) - st0 for x in sk[:, 0]])
