@@ -61,6 +61,7 @@ constexpr int SMEM = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
 enum : int { B_FULL_W = 0, B_FULL_H = STAGES, B_CONV = 2 * STAGES, B_EMPTY = 3 * STAGES, B_ACC_FULL = 4 * STAGES,
              B_ACC_EMPTY = 4 * STAGES + NBUF, B_P_READY = 4 * STAGES + 2 * NBUF, B_COUNT = 4 * STAGES + 2 * NBUF + 2 };
 static_assert(B_COUNT * 8 <= 240, "barrier area");
+static_assert(KG == 2, "flag polling reads the two step flags of a cluster as one 8-byte word");
 static_assert(UPC == BK, "one k-block of h = the units of exactly one cluster (flag indexing)");
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -159,12 +160,17 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 // each publish flags[cta] = number of steps completed.  Lanes poll different k-blocks in parallel.
                 if (lane == 0) GRU_TRACE_STEP(6);
                 for (int kb = lane; kb < NKB; kb += 32) {
+                    // both flags of the cluster with one relaxed 8-byte load per poll; one acquire fence at the end
                     const unsigned* fl = flags + (k0 / UPC + kb) * KG;
                     SpinGuard guard;
-#pragma unroll
-                    for (int r = 0; r < KG; ++r)
-                        while (ld_acquire_gpu(fl + r) < (unsigned)step) guard.tick();
+                    for (;;) {
+                        unsigned f0, f1;
+                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(f0), "=r"(f1) : "l"(fl) : "memory");
+                        if (f0 >= (unsigned)step && f1 >= (unsigned)step) break;
+                        guard.tick();
+                    }
                 }
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 __syncwarp();
                 fence_proxy_async();                   // generic-proxy writes of h -> async-proxy (TMA) reads
                 if (lane == 0) GRU_TRACE_STEP(0);
