@@ -210,6 +210,21 @@ int gait_crop_cam_to_orig_img(const float* cam, const void* bbox, int bbox_is_f6
 int gait_crop_coords_to_orig_img(const void* bbox, int bbox_is_f64, int64_t ldb, const float* keypoints, float* out, int64_t N,
                                  int J, int D, double crop_size, gait_stream_t stream);
 
+/* ---- heads next to the path ---------------------------------------- */
+/* KeypointAttention (lib/models/layers/keypoint_attention.py:34-55, act='softmax'): heat (B,J,HW) is scaled, soft-maxed over
+ * its HW pixels and used to pool feat (B,C,HW):  out[b*sob + c*soc + j*soj] = sum_hw softmax(heat[b,j])[hw] feat[b,c,hw]. */
+int gait_keypoint_attention(const float* feat, const float* heat, float scale, float* out, int64_t B, int C, int J, int HW,
+                            int64_t sob, int64_t soc, int64_t soj, gait_stream_t stream);
+/* LocallyConnected2d (lib/models/layers/locallyconnected2d.py:39-49) with kernel_size 1 and output_size [J,1]:
+ * out[n,o,j] = sum_c x[n,c,j] W[o,c,j] + bias[o,j]; every operand is addressed through element strides (s*), so a
+ * broadcast input (sxj = 0, gait_feat_encoder.py:88), a weight shared by all joints (swj = 0: a 1x1 convolution) and a
+ * transposed output need no copies.  Optional: out2 = out + resid (same layout as out). */
+int gait_locally_connected(const float* x, int64_t sxn, int64_t sxc, int64_t sxj, const float* W, int64_t swo, int64_t swc,
+                           int64_t swj, const float* bias, int64_t sbo, int64_t sbj, float* out, int64_t son, int64_t soo,
+                           int64_t soj, const float* resid, float* out2, int64_t N, int C, int O, int J, gait_stream_t stream);
+/* kind 0: LeakyReLU(slope), kind 1: Tanh (gait_feat_encoder.py:58-78). y may alias x. */
+int gait_activation(const float* x, float* y, int64_t n, int kind, float slope, gait_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

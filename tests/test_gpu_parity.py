@@ -543,3 +543,46 @@ def test_postproc_vs_oracle_long_and_empty(lib_loaded):
     kp = (rng.random((N, 25, 2)) * 2 - 1).astype(np.float32)
     assert np.array_equal(PP.convert_crop_cam_to_orig_img(cam, bbox, 1920, 1080), OP.convert_crop_cam_to_orig_img(cam, bbox, 1920, 1080))
     assert np.array_equal(PP.convert_crop_coords_to_orig_img(bbox, kp.copy(), 224), OP.convert_crop_coords_to_orig_img(bbox, kp.copy(), 224))
+
+
+# ------------------------------------------------------------------------------- heads next to the path
+def test_heads_vs_reference_golden(golden, lib_loaded):
+    """LocallyConnected2d, KeypointAttention, the PARE final-prediction head and BidirectionalModel against outputs of the
+    reference's own classes (tests/golden/make_golden_heads.py); FP32 tolerance 1e-5 (sums are ordered differently)."""
+    from gaitb200.layers import BidirectionalModel, KeypointAttention, LocallyConnected2d
+    from gaitb200.pare_final import PareFinalHead
+    g = golden("heads")
+    d = lambda k: torch.from_numpy(g[k]).cuda()
+    lc = LocallyConnected2d(128, 6, [24, 1], 1, 1).cuda()
+    lc.load_state_dict({"weight": d("lc_pose_w")})
+    assert maxerr(lc(d("lc_pose_x")), g["lc_pose_y"]) <= 2e-6 * np.abs(g["lc_pose_y"]).max()   # 128-term sums of O(1) products
+    lcb = LocallyConnected2d(3, 128, [24, 1], 1, 1, bias=True).cuda()
+    lcb.load_state_dict({"weight": d("lc_cp_w"), "bias": d("lc_cp_b")})
+    assert maxerr(lcb(d("lc_cp_x")), g["lc_cp_y"]) <= 2e-6 * np.abs(g["lc_cp_y"]).max()
+    with pytest.raises(NotImplementedError):
+        LocallyConnected2d(3, 4, [24, 1], 3, 1)
+    assert maxerr(KeypointAttention()(d("ka_feat"), d("ka_heat")), g["ka_out"]) <= 1e-6
+    assert maxerr(KeypointAttention(use_scale=True)(d("ka_feat"), d("ka_heat")), g["ka_out_scaled"]) <= 1e-6
+    # PARE final head: state dict straight from the reference PareHead
+    ph = PareFinalHead().cuda()
+    sd = {k[len("ph_sd_"):]: torch.from_numpy(g[k]) for k in g if k.startswith("ph_sd_")}
+    missing = ph.load_state_dict(sd, strict=True)
+    plf, csf = ph._get_local_feats(d("ph_smpl_feats"), d("ph_part_attn"))
+    assert maxerr(plf, g["ph_point_local_feat"]) <= 1e-6 and maxerr(csf, g["ph_cam_shape_feats"]) <= 1e-5
+    o = ph(plf, csf, {})
+    assert set(o) == {"pred_rotmat", "pred_cam", "pred_shape", "pred_rot6d", "pred_pose"}
+    assert maxerr(o["pred_rot6d"], g["ph_pred_rot6d"]) <= 1e-5 and maxerr(o["pred_rotmat"], g["ph_pred_rotmat"]) <= TOL_R
+    assert maxerr(o["pred_cam"], g["ph_pred_cam"]) <= 1e-5 and maxerr(o["pred_shape"], g["ph_pred_shape"]) <= 1e-5
+    ph.iterative_regression = True
+    o2 = ph(plf, csf, {}, inits={"pred_rot6d": d("ph_pred_rot6d"), "pred_shape": d("ph_pred_shape"), "pred_cam": d("ph_pred_cam")})
+    assert maxerr(o2["pred_rot6d"], g["ph_it_rot6d"]) <= 1e-5 and maxerr(o2["pred_cam"], g["ph_it_cam"]) <= 1e-5
+    assert maxerr(o2["pred_shape"], g["ph_it_shape"]) <= 1e-5
+    # BidirectionalModel: same state_dict keys / shapes as the reference class, weights from the shared seeded generator
+    bm = BidirectionalModel(seqlen=16, use_pareFeat=True).cuda().eval()
+    shapes = {k: tuple(int(x) for x in s.split(",")) for k, s in zip(g["bm_state_keys"], g["bm_state_shapes"])}
+    assert {k: tuple(v.shape) for k, v in bm.state_dict().items()} == shapes
+    bm.load_state_dict(synthetic.seeded_state(shapes, seed=5), strict=True)
+    y, p, xc = bm(d("bm_x"), d("bm_cparams"))
+    assert maxerr(y, g["bm_y"]) <= 1e-5 and maxerr(p, g["bm_p"]) <= 1e-5 and maxerr(xc[:, :, ::7], g["bm_xc"]) <= 1e-6
+    with pytest.raises(NotImplementedError):
+        BidirectionalModel(seqlen=16, use_pareFeat=False)

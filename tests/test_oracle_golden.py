@@ -142,3 +142,26 @@ def test_postproc_oracle_vs_reference_golden(golden, smpl_data):
         assert np.abs(v[:, ::53] - g[f"sp_{tag}_verts"]).max() <= 1e-6 and np.abs(j - g[f"sp_{tag}_joints"]).max() <= 1e-6
     v, p, j = P.smooth_pose(smpl_data, g["sp_quat"].copy(), g["sp_betas"], min_cutoff=0.01, beta=0.5, kinectv2=True)
     assert np.array_equal(p, g["sp_quat_pose"]) and np.abs(j - g["sp_quat_joints"]).max() <= 1e-6
+
+
+def test_heads_oracle_vs_reference_golden(golden):
+    """oracle/heads.py against the reference's own LocallyConnected2d / KeypointAttention / PareHead / BidirectionalModel."""
+    from oracle import heads as H
+    g = golden("heads")
+    t = lambda k: torch.from_numpy(g[k])
+    assert (H.locally_connected(t("lc_pose_x"), t("lc_pose_w")) - t("lc_pose_y")).abs().max() <= 1e-6
+    assert (H.locally_connected(t("lc_cp_x"), t("lc_cp_w"), t("lc_cp_b")) - t("lc_cp_y")).abs().max() <= 1e-6
+    assert (H.keypoint_attention(t("ka_feat"), t("ka_heat")) - t("ka_out")).abs().max() <= 1e-6
+    assert (H.keypoint_attention(t("ka_feat"), t("ka_heat"), True) - t("ka_out_scaled")).abs().max() <= 1e-6
+    sd = {k[len("ph_sd_"):]: t(k) for k in g if k.startswith("ph_sd_")}
+    o = H.pare_final(sd, t("ph_smpl_feats"), t("ph_part_attn"))
+    for k, gk in (("point_local_feat", "ph_point_local_feat"), ("cam_shape_feats", "ph_cam_shape_feats"), ("pred_rotmat", "ph_pred_rotmat"),
+                  ("pred_cam", "ph_pred_cam"), ("pred_shape", "ph_pred_shape"), ("pred_rot6d", "ph_pred_rot6d")):
+        assert (o[k] - t(gk)).abs().max() <= 1e-5, k
+    o2 = H.pare_final(sd, t("ph_smpl_feats"), t("ph_part_attn"), inits={"pred_rot6d": t("ph_pred_rot6d"), "pred_shape": t("ph_pred_shape"),
+                                                                        "pred_cam": t("ph_pred_cam")}, iterative=True)
+    assert (o2["pred_rot6d"] - t("ph_it_rot6d")).abs().max() <= 1e-5 and (o2["pred_cam"] - t("ph_it_cam")).abs().max() <= 1e-5
+    shapes = {k: tuple(int(x) for x in s.split(",")) for k, s in zip(g["bm_state_keys"], g["bm_state_shapes"])}
+    bsd = synthetic.seeded_state(shapes, seed=5)
+    y, p, xc = H.bidirectional_model(bsd, t("bm_x"), t("bm_cparams"))
+    assert (y - t("bm_y")).abs().max() <= 1e-5 and (p - t("bm_p")).abs().max() <= 1e-5 and (xc[:, :, ::7] - t("bm_xc")).abs().max() <= 1e-6

@@ -55,6 +55,9 @@ _SIGS = {
     "gait_one_euro_filter": [P, P, I64, I64, F64, F64, F64, P],
     "gait_crop_cam_to_orig_img": [P, P, I32, I64, F64, F64, P, I64, P],
     "gait_crop_coords_to_orig_img": [P, I32, I64, P, P, I64, I32, I32, F64, P],
+    "gait_keypoint_attention": [P, P, F32, P, I64, I32, I32, I32, I64, I64, I64, P],
+    "gait_locally_connected": [P, I64, I64, I64, P, I64, I64, I64, P, I64, I64, P, I64, I64, I64, P, P, I64, I32, I32, I32, P],
+    "gait_activation": [P, P, I64, I32, F32, P],
     "gait_pack_theta": [P, P, I64, P, I64, P, I64, P],
 }
 _RESTYPES = {

@@ -168,3 +168,14 @@ def make_pose_inputs(num_frames: int, seed: int = 0, noise: float = 0.3):
         0.2 * torch.randn(num_frames, generator=g),
         0.2 * torch.randn(num_frames, generator=g)], dim=1)
     return rot6d, betas, cam
+
+
+def seeded_state(shapes: dict, seed: int = 0, scale: float = 0.05) -> dict:
+    """Deterministic stand-in for a checkpoint: one U(-scale, scale) tensor per (key, shape), generated key by key in
+    sorted order from its own seeded generator - so a golden-vector script and a test can build the same weights from
+    nothing but the state_dict keys and shapes (used for BidirectionalModel, whose 30 MB of GRU weights are not committed)."""
+    out = {}
+    for i, k in enumerate(sorted(shapes)):
+        g = torch.Generator().manual_seed(seed * 100003 + i)
+        out[k] = (torch.rand(tuple(shapes[k]), generator=g) * 2 - 1) * scale
+    return out

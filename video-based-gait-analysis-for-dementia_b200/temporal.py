@@ -16,9 +16,10 @@ import torch.nn as nn
 from . import _lib as L
 
 
-def gru_forward(gru: nn.GRU, x: torch.Tensor, resid: torch.Tensor | None = None):
+def gru_forward(gru: nn.GRU, x: torch.Tensor, resid: torch.Tensor | None = None, return_hn: bool = False):
     """nn.GRU forward (h0 = 0) on x laid out (S,T,I) contiguous.  Returns (y (S,T,H*dirs), out)
-    where out = y + resid when `resid` (S,T,H) is given and the GRU is single-direction."""
+    where out = y + resid when `resid` (S,T,H) is given and the GRU is single-direction; with `return_hn` a third
+    value h_n (num_layers*dirs, S, H) in torch's order (layer-major, forward before reverse)."""
     if gru.training and gru.dropout > 0 and gru.num_layers > 1:
         raise L.GaitLibraryError("GRU kernels implement eval() semantics (no inter-layer dropout); call .eval()")
     x = L.f32(x, "x")
@@ -28,6 +29,7 @@ def gru_forward(gru: nn.GRU, x: torch.Tensor, resid: torch.Tensor | None = None)
     nbytes = L.load().gait_gru_workspace_bytes(S, T, H)
     ws = torch.empty(max(nbytes, 4) // 4, device=dev)
     inp, out = x, None
+    hn = torch.empty(gru.num_layers * dirs, S, H, device=dev) if return_hn else None
     for layer in range(gru.num_layers):
         y = torch.empty(S, T, H * dirs, device=dev)
         last = layer == gru.num_layers - 1
@@ -46,9 +48,12 @@ def gru_forward(gru: nn.GRU, x: torch.Tensor, resid: torch.Tensor | None = None)
             L.call("gait_gru_layer", L.ptr(inp), inp.shape[-1], L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih), L.ptr(b_hh),
                    None, y.data_ptr() + 4 * d * H, H * dirs,
                    L.ptr(resid) if fuse_res else None, resid.shape[-1] if fuse_res else 0,
-                   L.ptr(out) if fuse_res else None, H if fuse_res else 0, None,
+                   L.ptr(out) if fuse_res else None, H if fuse_res else 0,
+                   None if hn is None else hn[layer * dirs + d].data_ptr(),
                    S, T, inp.shape[-1], H, d, L.ptr(ws), nbytes, L.stream_ptr())
         inp = y
+    if return_hn:
+        return inp, out, hn
     return inp, out
 
 
