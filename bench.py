@@ -284,11 +284,11 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # ---- end to end through the public API: pinned host features -> H2D -> step -> D2H of every output.
     # GaitHead.run_host_batches overlaps copy-in / kernels / copy-out of consecutive batches (two buffer slots).
     outs = head.outputs()
-    host_outs = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()} for _ in range(2)]
+    host_outs = [head.alloc_host_outputs() for _ in range(2)]
     feats_hosts = [feats_host, feats_host.clone().pin_memory()]
     h2d = feats_host.numel() * 4
     d2h = sum(v.numel() * 4 for v in host_outs[0].values())
-    e2e_steps = max(6, args.steps // 4)
+    e2e_steps = max(24, args.steps // 2)
     ins = [feats_hosts[i % 2] for i in range(e2e_steps)]
     hos = [host_outs[i % 2] for i in range(e2e_steps)]
     head.run_host_batches(ins[:4], hos[:4])                    # warm-up
@@ -358,7 +358,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "d2h_gbs": d2h / (e2e_ms * 1e-3) / 1e9,
                 "host_vs_device_max_abs_diff": e2e_check,
-                "note": "GaitHead.run_host_batches: copy-in / kernels / copy-out of consecutive batches overlap on 3 streams"},
+                "note": "GaitHead.run_host_batches: copy-in / kernels / copy-out of consecutive batches overlap on 3 streams; "
+                        "D2H = mesh + one packed buffer of the small outputs; PCIe D2H measured ceiling on this box ~57 GB/s"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": roofline,

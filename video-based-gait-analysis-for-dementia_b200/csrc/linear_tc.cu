@@ -134,7 +134,16 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // lo part of the split whose hi part is the raw word (read truncated by the tensor core)
-__device__ __forceinline__ float tf32_lo(float x) { return tf32_hi(x - tf32_trunc(x)); }
+#ifndef GAIT_LO_ROUND
+#define GAIT_LO_ROUND 1       // 1: lo = RN_tf32(x - trunc(x)) (|x - hi - lo| <= 2^-22 |x|); 0: lo = x - trunc(x), read truncated (2^-20)
+#endif
+__device__ __forceinline__ float tf32_lo(float x) {
+#if GAIT_LO_ROUND
+    return tf32_hi(x - tf32_trunc(x));
+#else
+    return x - tf32_trunc(x);
+#endif
+}
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));

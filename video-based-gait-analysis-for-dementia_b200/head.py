@@ -21,6 +21,28 @@ from .temporal import TemporalEncoder
 _STATE_LD = 160
 
 
+# small per-frame outputs packed into one buffer: (plan key, output key, per-frame shape); segments start 16-byte aligned
+_SMALL = (("rotmat", "rotmat", (24, 3, 3)), ("joints", "kp_3d", (29, 3)), ("kp2d", "kp_2d", (29, 2)), ("kinect", "kinect25", (25, 3)),
+          ("theta", "theta", (85,)))
+
+
+def _small_layout(F: int):
+    """[(plan key, output key, shape, offset, numel)], total floats."""
+    out, off = [], 0
+    for key, name, shape in _SMALL:
+        n = F
+        for d in shape:
+            n *= d
+        out.append((key, name, shape, off, n))
+        off += (n + 3) // 4 * 4
+    return out, max(off, 4)
+
+
+class HostOutputs(dict):
+    """dict of pinned host tensors from GaitHead.alloc_host_outputs(); `.packed_small` is the buffer behind the small ones."""
+    packed_small = None
+
+
 class GaitHead(nn.Module):
     def __init__(self, smpl_data, mean_params, regressor_state=None, gru_state=None, write_mesh=True,
                  n_iter=3, **encoder_kw):
@@ -59,7 +81,7 @@ class GaitHead(nn.Module):
             "S": S, "T": T, "F": F, "V": V, "dev": dev,
             "x": e(S, T, H), "y_raw": e(S, T, H), "enc": e(S, T, H),
             "ws": e(max(gru_bytes, hmr_bytes, 4) // 4), "gru_bytes": gru_bytes, "hmr_bytes": hmr_bytes,
-            "state": e(F, _STATE_LD), "rotmat": e(F, 24, 3, 3), "Jp": e(F, 24, 3),
+            "state": e(F, _STATE_LD), "Jp": e(F, 24, 3),
             "aop": e(lib.gait_smpl_lbs_aop_bytes(F) // 4),
             "coef": e(F, 224), "v_posed": e(F, 384 * ((V + 127) // 128)),
             # full mesh (F,V,3), or in joints-only mode just the landmark vertices the joint sets read (config 5)
@@ -67,10 +89,28 @@ class GaitHead(nn.Module):
             "lm_verts": None if self.write_mesh else e(F, self.regressor.smpl._prepare()["n_landmarks"], 3),
             "lm_iota": None if self.write_mesh else torch.arange(self.regressor.smpl._prepare()["n_landmarks"], dtype=torch.int32, device=dev),
             "extra": e((V + 127) // 128, F, 1, 3),
-            "joints": e(F, 29, 3), "kp2d": e(F, 29, 2), "kinect": e(F, 25, 3), "theta": e(F, 85),
+            # the small per-frame outputs live in ONE buffer, so the host copy of a step is two transfers (mesh + this)
+            "small": e(_small_layout(F)[1]),
             "gather": torch.tensor(SPIN2_TO_KINECTV2, dtype=torch.int32, device=dev),
         }
+        for key, _, shape, off, n in _small_layout(F)[0]:
+            p[key] = p["small"][off:off + n].view(F, *shape)
         return p
+
+    def alloc_host_outputs(self):
+        """Pinned host buffers for run_host_batches: a dict with the keys/shapes of outputs(); the small outputs are views of
+        one pinned buffer laid out like the device-side one, so they arrive with a single D2H transfer."""
+        p = self._plan
+        S, T, F = p["S"], p["T"], p["F"]
+        layout, total = _small_layout(F)
+        small = torch.empty(total).pin_memory()
+        out = HostOutputs()
+        out.packed_small = small
+        for _, name, shape, off, n in layout:
+            out[name] = small[off:off + n].view(S, T, *shape)
+        if self.write_mesh:
+            out["verts"] = torch.empty(S, T, p["V"], 3).pin_memory()
+        return out
 
     def plan(self, S: int, T: int, slots: int = 1):
         """Allocate `slots` independent buffer sets for (S,T) (slot 0 is the default one; a second
@@ -235,8 +275,13 @@ class GaitHead(nn.Module):
             ev_cmp[k] = cur.record_event()
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp[k])
-                for key, v in self.outputs(k).items():
-                    out_host[key].copy_(v, non_blocking=True)
+                if isinstance(out_host, HostOutputs):
+                    if self.write_mesh:
+                        out_host["verts"].copy_(self.outputs(k)["verts"], non_blocking=True)
+                    out_host.packed_small.copy_(p["small"], non_blocking=True)
+                else:
+                    for key, v in self.outputs(k).items():
+                        out_host[key].copy_(v, non_blocking=True)
                 ev_out[k] = s_out.record_event()
         cur.wait_stream(s_out)
         cur.wait_stream(s_in)
