@@ -68,7 +68,7 @@ int gait_relu(const float* x, float* y, int64_t n, gait_stream_t stream) {
 
 size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H) {
     if (S <= 0 || T <= 0 || H <= 0) return 0;
-    return (size_t)(S * T * 3 * H + kGruMaxSplits * S * 3 * H) * sizeof(float) + 4 * (size_t)(H / 16 + 64);   // + per-CTA step flags of the persistent kernel
+    return (size_t)(S * T * 3 * H + kGruMaxSplits * S * 3 * H) * sizeof(float) + 128 * (size_t)(H / 16 + 2);   // + per-CTA step flags (one 128-byte line each) of the persistent kernel
 }
 
 int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* W_hh, const float* b_ih,

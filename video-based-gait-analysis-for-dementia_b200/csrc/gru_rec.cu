@@ -15,8 +15,8 @@
 //     The tensor core truncates when it adds into its FP32 accumulator, so every 64 k the partial sum is drained
 //     (tcgen05.ld) and added round-to-nearest into FP32 registers (same scheme as linear_tc.cu).
 //   * end of step: hi + lo rows are combined through shared memory, the two K-slice partials through
-//     distributed shared memory (mbarrier handshake, no cluster-wide barrier); each CTA then finalises 16 units
-//     x 64 sequences: gates, h_t, h_t + residual, with h_{t-1} kept in registers.
+//     distributed shared memory (mbarrier handshake, no cluster-wide barrier); each CTA then finalises the 32 units
+//     of the cluster for 32 of the 64 sequences: gates, h_t, h_t + residual, with h_{t-1} kept in registers.
 //   * h_t goes to y (the API output) and is read back by TMA at the next step.  There is no grid-wide barrier:
 //     k-block kb of a K-slice needs exactly the 32 units one cluster produces, so every CTA publishes a step
 //     flag (st.release.gpu) and the h producer polls the KG flags of that cluster (ld.acquire.gpu) before the
@@ -61,7 +61,8 @@ constexpr int SMEM = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
 enum : int { B_FULL_W = 0, B_FULL_H = STAGES, B_CONV = 2 * STAGES, B_EMPTY = 3 * STAGES, B_ACC_FULL = 4 * STAGES,
              B_ACC_EMPTY = 4 * STAGES + NBUF, B_P_READY = 4 * STAGES + 2 * NBUF, B_COUNT = 4 * STAGES + 2 * NBUF + 2 };
 static_assert(B_COUNT * 8 <= 240, "barrier area");
-static_assert(KG == 2, "flag polling reads the two step flags of a cluster as one 8-byte word");
+constexpr int FLAG_STRIDE = 32;             // words between the step flags of consecutive CTAs (one 128-byte line each)
+static_assert(KG == 2, "flag polling reads the two step flags of a cluster");
 static_assert(UPC == BK, "one k-block of h = the units of exactly one cluster (flag indexing)");
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -160,12 +161,14 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 // each publish flags[cta] = number of steps completed.  Lanes poll different k-blocks in parallel.
                 if (lane == 0) GRU_TRACE_STEP(6);
                 for (int kb = lane; kb < NKB; kb += 32) {
-                    // both flags of the cluster with one relaxed 8-byte load per poll; one acquire fence at the end
-                    const unsigned* fl = flags + (k0 / UPC + kb) * KG;
+                    // relaxed polls, one acquire fence at the end; every CTA's flag has its own 128-byte line (the two
+                    // release stores of a cluster and the polls of 64 readers otherwise meet in one L2 sector)
+                    const unsigned* fl = flags + (size_t)(k0 / UPC + kb) * KG * FLAG_STRIDE;
                     SpinGuard guard;
                     for (;;) {
                         unsigned f0, f1;
-                        asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(f0), "=r"(f1) : "l"(fl) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f0) : "l"(fl) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(f1) : "l"(fl + FLAG_STRIDE) : "memory");
                         if (f0 >= (unsigned)step && f1 >= (unsigned)step) break;
                         guard.tick();
                     }
@@ -284,9 +287,11 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         const int q = warp & 3;                            // TMEM lane quadrant of this warp
         const int hf = (warp - 4) >> 2;                    // which 48 of the 96 accumulator columns
         const int prow = (q * 32 + lane) & 63;             // sequence of this thread's TMEM lane (lanes 64+ = lo rows)
-        // finalisation: thread -> (sequence, 4 consecutive hidden units)
-        const int seq = pt >> 2, u4 = pt & 3;
-        const int ucol = (int)kr * UC + u4 * 4;            // column inside a gate's 32-wide block of P
+        // finalisation: thread -> (sequence, 4 consecutive hidden units).  CTA kr of the cluster finalises all 32 units of
+        // the cluster for sequences 32*kr .. 32*kr+31, so every row it reads (gi, resid) or writes (y, out) is a whole
+        // 128-byte line that no other CTA touches.
+        const int seq = (int)kr * (SB / KG) + (pt >> 3), u4 = pt & 7;
+        const int ucol = u4 * 4;                           // column inside a gate's 32-wide block of P
         const int unit = u0 + ucol;
         const bool act = seq < S;
         float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -382,7 +387,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             if (step < T - 1) {
                 fence_proxy_async_global();            // generic-proxy stores of h_t -> async-proxy (TMA) reads by other CTAs
                 named_bar_sync(1, NPROM);
-                if (pt == 0) st_release_gpu(flags + blockIdx.x, (unsigned)(step + 1));
+                if (pt == 0) st_release_gpu(flags + (size_t)blockIdx.x * FLAG_STRIDE, (unsigned)(step + 1));
             }
             if (pt == 0) GRU_TRACE_STEP(5);
             if (trace && pt == 0 && step == 3) trace[1024 + blockIdx.x * 2] = global_timer_ns();
@@ -444,7 +449,7 @@ int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, 
                                     BK, 1, SB / 2, true));
     if (h0) GAIT_TRY(make_tensor_map_3d_f32(&tmH0, h0, (uint64_t)H, 1, (uint64_t)S, (uint64_t)H * 4, (uint64_t)H * 4, BK, 1, SB / 2, true));
     else tmH0 = tmY;
-    GAIT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * (size_t)(H / UC), stream));   // per-CTA step flags
+    GAIT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int) * (size_t)(H / UC) * FLAG_STRIDE, stream));   // per-CTA step flags
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(H / UC));
     cfg.blockDim = dim3(THREADS);
