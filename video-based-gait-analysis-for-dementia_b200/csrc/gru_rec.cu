@@ -78,9 +78,11 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // debug timestamps of CTA 0: trace[step*8 + i] (step < 32) and trace[256 + kb*8 + i] for the k-blocks of step 2
-#define GRU_TRACE_STEP(i) do { if (trace && blockIdx.x == 0 && step < 32) trace[step * 8 + (i)] = clock64(); } while (0)
-#define GRU_TRACE_KB(i) do { if (trace && blockIdx.x == 0 && step == 2 && kb < 64) trace[256 + kb * 8 + (i)] = clock64(); } while (0)
+#define GRU_TRACE_STEP(i) do { if (TRACE && trace && blockIdx.x == 0 && step < 32) trace[step * 8 + (i)] = clock64(); } while (0)
+#define GRU_TRACE_KB(i) do { if (TRACE && trace && blockIdx.x == 0 && step == 2 && kb < 64) trace[256 + kb * 8 + (i)] = clock64(); } while (0)
 
+// TRACE = true is the instrumented build (gait_debug_gru_trace); the product launches TRACE = false
+template <bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
                      const __grid_constant__ CUtensorMap tmH0, const float* __restrict__ gi,
@@ -177,7 +179,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 __syncwarp();
                 fence_proxy_async();                   // generic-proxy writes of h -> async-proxy (TMA) reads
                 if (lane == 0) GRU_TRACE_STEP(0);
-                if (trace && lane == 0 && step == 4) trace[1024 + blockIdx.x * 2 + 1] = global_timer_ns();   // skew probe, all CTAs
+                if (TRACE && trace && lane == 0 && step == 4) trace[1024 + blockIdx.x * 2 + 1] = global_timer_ns();   // skew probe, all CTAs
             }
             // four lanes issue the 2 x 2 boxes (32 sequences each) of two k-blocks at a time
             for (int kb0 = 0; kb0 < NKB; kb0 += 2) {
@@ -390,7 +392,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (pt == 0) st_release_gpu(flags + (size_t)blockIdx.x * FLAG_STRIDE, (unsigned)(step + 1));
             }
             if (pt == 0) GRU_TRACE_STEP(5);
-            if (trace && pt == 0 && step == 3) trace[1024 + blockIdx.x * 2] = global_timer_ns();
+            if (TRACE && trace && pt == 0 && step == 3) trace[1024 + blockIdx.x * 2] = global_timer_ns();
         }
     }
     tc_fence_before();
@@ -415,8 +417,9 @@ static int max_coresident_ctas() {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = KG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (cudaFuncSetAttribute(gru_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
-        cudaOccupancyMaxActiveClusters(&n_clusters, gru_recurrent_kernel, &cfg) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gru_recurrent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(gru_recurrent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n_clusters, gru_recurrent_kernel<false>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         n_clusters = 0;
     }
@@ -469,13 +472,14 @@ int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, 
         coop = (e && atoi(e) == 0) ? 0 : 1;
     }
     cfg.numAttrs = coop ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gru_recurrent_kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out,
+    auto kernel = g_trace ? gru_recurrent_kernel<true> : gru_recurrent_kernel<false>;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out,
                                        ldout, hn, (int)S, (int)T, (int)H, reverse, counter, g_trace);
     if (e != cudaSuccess && coop) {
         cudaGetLastError();
         coop = 0;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, gru_recurrent_kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out, ldout,
+        e = cudaLaunchKernelEx(&cfg, kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out, ldout,
                                hn, (int)S, (int)T, (int)H, reverse, counter, g_trace);
     }
     if (e != cudaSuccess) {
