@@ -79,6 +79,6 @@ bool gru_recurrent_eligible(const float* gi, const float* W_hh, const float* h0,
                             int64_t H);
 int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, const float* h0, float* y, int64_t ldy,
                          const float* resid, int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T,
-                         int64_t H, int reverse, unsigned int* counter, cudaStream_t stream);
+                         int64_t H, int reverse, unsigned int* counter, float* hlo, cudaStream_t stream);
 
 }  // namespace gait

@@ -68,7 +68,8 @@ int gait_relu(const float* x, float* y, int64_t n, gait_stream_t stream) {
 
 size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H) {
     if (S <= 0 || T <= 0 || H <= 0) return 0;
-    return (size_t)(S * T * 3 * H + kGruMaxSplits * S * 3 * H) * sizeof(float) + 128 * (size_t)(H / 16 + 2);   // + per-CTA step flags (one 128-byte line each) of the persistent kernel
+    return (size_t)(S * T * 3 * H + kGruMaxSplits * S * 3 * H) * sizeof(float) + 128 * (size_t)(H / 16 + 2)
+           + (size_t)(2 * S * H) * sizeof(float);   // + per-CTA step flags (one 128-byte line each) and the h_lo scratch of the persistent kernel
 }
 
 int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* W_hh, const float* b_ih,
@@ -101,7 +102,9 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
     if (gru_path != 1 && linear_path() != 1) {
         if (gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S, T, H)) {
             unsigned int* counter = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);
-            return gru_recurrent_launch(gi, W_hh, b_hh, h0, y, ldy, resid, ldres, out, ldout, hn, S, T, H, reverse, counter, st);
+            uintptr_t lo_addr = (reinterpret_cast<uintptr_t>(counter) + 128 * (size_t)(H / 16 + 1) + 127) & ~(uintptr_t)127;
+            return gru_recurrent_launch(gi, W_hh, b_hh, h0, y, ldy, resid, ldres, out, ldout, hn, S, T, H, reverse, counter,
+                                        reinterpret_cast<float*>(lo_addr), st);
         }
         if (gru_path == 2) {
             set_error("gru_layer: persistent recurrent kernel not eligible for S=%lld T=%lld H=%lld", (long long)S, (long long)T, (long long)H);

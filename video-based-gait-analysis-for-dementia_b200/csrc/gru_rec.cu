@@ -39,12 +39,13 @@ constexpr int UPC = UC * KG;                // hidden units per cluster
 constexpr int NB = 3 * UPC;                 // W_hh rows per CTA (UMMA N) = 96
 constexpr int SB = 64;                      // sequences (A rows: 64 hi + 64 lo = UMMA M 128)
 constexpr int BK = 32;                      // floats per k-block = one 128-byte swizzle span
-constexpr int STAGES = 5;
+constexpr int STAGES = 4;
 constexpr int H_TILE = SB * BK * 4;         //  8 192 B raw h tile
 
 constexpr int G_TILE = UPC * BK * 4;        //  4 096 B: one gate's rows = one TMA box
 constexpr int W_TILE = NB * BK * 4;         // 12 288 B
-constexpr int STAGE = H_TILE + 2 * W_TILE;  // 32 768 B: [h raw | W raw = hi | W lo]
+constexpr int A_TILE = 2 * H_TILE;          // 16 384 B: [h raw = hi (64 rows) | h lo (64 rows)], both loaded by TMA
+constexpr int STAGE = A_TILE + 2 * W_TILE;  // 40 960 B: [h hi | h lo | W raw = hi | W lo]
 constexpr int PLD = 100;                    // row stride (floats) of the partial-sum buffer: conflict-free float4 rows
 constexpr int P_FLOATS = SB * PLD;
 constexpr int NBUF = 3;                     // TMEM accumulator ring (3 x 96 columns)
@@ -85,7 +86,8 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float
 template <bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmY,
-                     const __grid_constant__ CUtensorMap tmH0, const float* __restrict__ gi,
+                     const __grid_constant__ CUtensorMap tmH0, const __grid_constant__ CUtensorMap tmL, float* hlo,
+                     const float* __restrict__ gi,
                      const float* __restrict__ b_hh, const float* __restrict__ h0, float* y, int64_t ldy,
                      const float* __restrict__ resid, int64_t ldres, float* __restrict__ out, int64_t ldout,
                      float* __restrict__ hn, int S, int T, int H, int reverse, unsigned* flags,
@@ -108,7 +110,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(BAR(B_FULL_W + s), 3);           // one 32-row box per gate, each issued by its own lane
-            mbar_init(BAR(B_FULL_H + s), 2);           // two 32-sequence boxes
+            mbar_init(BAR(B_FULL_H + s), 4);           // h and h_lo, two 32-sequence boxes each
             mbar_init(BAR(B_CONV + s), NCONV / 32);       // one arrival per converter warp
             mbar_init(BAR(B_EMPTY + s), 1);
         }
@@ -147,7 +149,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (lane < 3) {
                     if (lane == 0) GRU_TRACE_KB(0);
                     mbar_arrive_expect_tx(BAR(B_FULL_W + s), G_TILE);
-                    tma_load_2d(base + s * STAGE + H_TILE + lane * G_TILE, &tmW, k0 + kb * BK, lane * H + u0, BAR(B_FULL_W + s));
+                    tma_load_2d(base + s * STAGE + A_TILE + lane * G_TILE, &tmW, k0 + kb * BK, lane * H + u0, BAR(B_FULL_W + s));
                 }
                 __syncwarp();
             }
@@ -181,17 +183,20 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (lane == 0) GRU_TRACE_STEP(0);
                 if (TRACE && trace && lane == 0 && step == 4) trace[1024 + blockIdx.x * 2 + 1] = global_timer_ns();   // skew probe, all CTAs
             }
-            // four lanes issue the 2 x 2 boxes (32 sequences each) of two k-blocks at a time
+            // eight lanes issue the boxes of two k-blocks at a time: {h (= hi), h_lo} x {sequences 0-31, 32-63}.
+            // h_lo of the previous step sits in slot (step-1)&1 of the scratch the finalising threads write.
+            const int lslot = (step - 1) & 1;
             for (int kb0 = 0; kb0 < NKB; kb0 += 2) {
-                const int kb = kb0 + (lane >> 1), half = lane & 1;
-                if (lane < 4 && kb < NKB) {
-                    const int my = it + (lane >> 1), s = my % STAGES;
+                const int kb = kb0 + (lane >> 2), part = (lane >> 1) & 1, half = lane & 1;
+                if (lane < 8 && kb < NKB) {
+                    const int my = it + (lane >> 2), s = my % STAGES;
                     const uint32_t ph = (my / STAGES) & 1;
                     mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
-                    if (half == 0) GRU_TRACE_KB(1);
+                    if ((lane & 3) == 0) GRU_TRACE_KB(1);
                     mbar_arrive_expect_tx(BAR(B_FULL_H + s), H_TILE / 2);
-                    const uint32_t dst = base + s * STAGE + half * (H_TILE / 2);
-                    if (step == 0) tma_load_3d(dst, &tmH0, k0 + kb * BK, 0, half * (SB / 2), BAR(B_FULL_H + s));
+                    const uint32_t dst = base + s * STAGE + part * H_TILE + half * (H_TILE / 2);
+                    if (part) tma_load_3d(dst, &tmL, k0 + kb * BK, lslot, half * (SB / 2), BAR(B_FULL_H + s));
+                    else if (step == 0) tma_load_3d(dst, &tmH0, k0 + kb * BK, 0, half * (SB / 2), BAR(B_FULL_H + s));
                     else tma_load_3d(dst, &tmY, k0 + kb * BK, tp, half * (SB / 2), BAR(B_FULL_H + s));
                 }
                 __syncwarp();
@@ -216,7 +221,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 const uint32_t acc = tmem_d + (uint32_t)(buf * NB);
                 const uint32_t st = base + s * STAGE;
                 const uint32_t a = tmem_d + (uint32_t)(TMEM_A + s * BK);
-                const uint64_t b_hi = make_sdesc_sw128(st + H_TILE), b_lo = make_sdesc_sw128(st + H_TILE + W_TILE);
+                const uint64_t b_hi = make_sdesc_sw128(st + A_TILE), b_lo = make_sdesc_sw128(st + A_TILE + W_TILE);
                 const bool last_of_chunk = (kb % DRAIN_KB) == DRAIN_KB - 1 || kb == NKB - 1;
                 if (elect_one()) {
 #pragma unroll
@@ -240,15 +245,15 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         // into tensor memory - lanes 0-63 get the raw words (hi), lanes 64-127 the lo parts.
         const int ct = threadIdx.x - (128 + NPROM);
         const int quad = warp & 3, half = (warp - 12) >> 2;           // TMEM lane quadrant / which 16 of the 32 columns
-        const int arow = quad * 32 + lane, hseq = arow & 63;          // A row = TMEM lane; source sequence
+        const int arow = quad * 32 + lane;                            // A row = TMEM lane = row of the stage's A tile
         int it = 0;
         for (int step = first_gemm; step < T; ++step) {
             for (int kb = 0; kb < NKB; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 uint8_t* st = gbase + s * STAGE;
-                const float4* w_hi = reinterpret_cast<const float4*>(st + H_TILE) + ct;
-                float4* w_lo = reinterpret_cast<float4*>(st + H_TILE + W_TILE) + ct;
+                const float4* w_hi = reinterpret_cast<const float4*>(st + A_TILE) + ct;
+                float4* w_lo = reinterpret_cast<float4*>(st + A_TILE + W_TILE) + ct;
                 constexpr int NW = W_TILE / 16 / NCONV;               // 3
                 mbar_wait(BAR(B_FULL_W + s), ph);
                 if (ct == 0) GRU_TRACE_KB(4);
@@ -261,17 +266,15 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 mbar_wait(BAR(B_FULL_H + s), ph);
                 if (ct == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
                 {
-                    const float4* hrow = reinterpret_cast<const float4*>(st + hseq * (BK * 4));
+                    // A row (0-63: h = hi, 64-127: h_lo written by the finalising threads of the previous step): a plain
+                    // shared-memory -> tensor-memory move, no arithmetic
+                    const float4* hrow = reinterpret_cast<const float4*>(st + arow * (BK * 4));
                     uint32_t r[16];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float4 x = hrow[(half * 4 + c) ^ (hseq & 7)];     // un-swizzle
+                        const float4 x = hrow[(half * 4 + c) ^ (arow & 7)];     // un-swizzle
                         r[4 * c] = __float_as_uint(x.x); r[4 * c + 1] = __float_as_uint(x.y);
                         r[4 * c + 2] = __float_as_uint(x.z); r[4 * c + 3] = __float_as_uint(x.w);
-                    }
-                    if (quad >= 2) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(tf32_lo(__uint_as_float(r[j])));
                     }
                     tmem_st16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TMEM_A + s * BK + half * 16), r);
                 }
@@ -385,6 +388,9 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 *reinterpret_cast<float4*>(y + f * ldy + unit) = h;
                 if (out) *reinterpret_cast<float4*>(out + f * ldout + unit) = f4_add(h, rs);
                 if (hn && step == T - 1) *reinterpret_cast<float4*>(hn + (int64_t)seq * H + unit) = h;
+                if (step < T - 1)          // lo half of the next step's A operand (hi = h itself, read truncated)
+                    *reinterpret_cast<float4*>(hlo + ((int64_t)seq * 2 + (step & 1)) * H + unit) =
+                        make_float4(tf32_lo(h.x), tf32_lo(h.y), tf32_lo(h.z), tf32_lo(h.w));
             }
             if (step < T - 1) {
                 fence_proxy_async_global();            // generic-proxy stores of h_t -> async-proxy (TMA) reads by other CTAs
@@ -401,6 +407,14 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
     }
     cluster_sync_all();                                // nobody leaves while a peer may still read its partials
+}
+
+// h0 given by the caller: lo half of step 0's A operand into scratch slot 1 (= (0 - 1) & 1)
+__global__ void split_h0_lo_kernel(const float* __restrict__ h0, float* __restrict__ hlo, int64_t S, int64_t H) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= S * H) return;
+    const int64_t s = i / H, u = i % H;
+    hlo[(s * 2 + 1) * H + u] = tf32_lo(h0[i]);
 }
 
 unsigned long long* g_trace = nullptr;
@@ -443,10 +457,17 @@ bool gru_recurrent_eligible(const float* gi, const float* W_hh, const float* h0,
 
 int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, const float* h0, float* y, int64_t ldy,
                          const float* resid, int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T,
-                         int64_t H, int reverse, unsigned int* counter, cudaStream_t stream) {
+                         int64_t H, int reverse, unsigned int* counter, float* hlo, cudaStream_t stream) {
     using namespace grurec;
     GAIT_REQUIRE(aligned16(b_hh) && (!hn || aligned16(hn)), "gru(persistent): b_hh / hn must be 16-byte aligned");
-    CUtensorMap tmW, tmY, tmH0;
+    GAIT_REQUIRE(aligned16(hlo), "gru(persistent): scratch must be 16-byte aligned");
+    CUtensorMap tmW, tmY, tmH0, tmL;
+    // h_lo scratch (S, 2, H): slot = step parity
+    GAIT_TRY(make_tensor_map_3d_f32(&tmL, hlo, (uint64_t)H, 2, (uint64_t)S, (uint64_t)H * 4, (uint64_t)(2 * H) * 4, BK, 1, SB / 2, true));
+    if (h0) {
+        split_h0_lo_kernel<<<(unsigned)ceil_div(S * H, 256), 256, 0, stream>>>(h0, hlo, S, H);
+        GAIT_TRY(check_launch("gru(h0 split)"));
+    }
     GAIT_TRY(make_tensor_map_2d(&tmW, 4, W_hh, (uint64_t)H, (uint64_t)(3 * H), (uint64_t)H * 4, BK, UPC, true));
     GAIT_TRY(make_tensor_map_3d_f32(&tmY, y, (uint64_t)H, (uint64_t)T, (uint64_t)S, (uint64_t)ldy * 4, (uint64_t)(T * ldy) * 4,
                                     BK, 1, SB / 2, true));
@@ -473,13 +494,13 @@ int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, 
     }
     cfg.numAttrs = coop ? 2 : 1;
     auto kernel = g_trace ? gru_recurrent_kernel<true> : gru_recurrent_kernel<false>;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmW, tmY, tmH0, tmL, hlo, gi, b_hh, h0, y, ldy, resid, ldres, out,
                                        ldout, hn, (int)S, (int)T, (int)H, reverse, counter, g_trace);
     if (e != cudaSuccess && coop) {
         cudaGetLastError();
         coop = 0;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kernel, tmW, tmY, tmH0, gi, b_hh, h0, y, ldy, resid, ldres, out, ldout,
+        e = cudaLaunchKernelEx(&cfg, kernel, tmW, tmY, tmH0, tmL, hlo, gi, b_hh, h0, y, ldy, resid, ldres, out, ldout,
                                hn, (int)S, (int)T, (int)H, reverse, counter, g_trace);
     }
     if (e != cudaSuccess) {
