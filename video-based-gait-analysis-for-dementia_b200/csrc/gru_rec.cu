@@ -21,8 +21,8 @@
 //     k-block kb of a K-slice needs exactly the 32 units one cluster produces, so every CTA publishes a step
 //     flag (st.release.gpu) and the h producer polls the KG flags of that cluster (ld.acquire.gpu) before the
 //     TMA load; the W tiles of the next step are prefetched and converted while those flags are awaited.
-// Warp roles: 0 and 3 = W TMA producers (even / odd k-blocks), 1 = MMA issuer + TMEM owner, 2 = h TMA producer (polls the flags),
-// 4-11 = promotion + gates (256 threads), 12-19 = FP32 -> TF32 hi/lo converters (256 threads).
+// Warp roles: 0 = W TMA producer, 1 and 3 = MMA issuers (even / odd accumulator chunks; 1 owns TMEM), 2 = h TMA producer (polls the flags),
+// 4-11 = promotion + gates (256 threads), 12-19 = converters (two groups of 4 warps alternating k-blocks).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -111,7 +111,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(BAR(B_FULL_W + s), 3);           // one 32-row box per gate, each issued by its own lane
             mbar_init(BAR(B_FULL_H + s), 4);           // h and h_lo, two 32-sequence boxes each
-            mbar_init(BAR(B_CONV + s), NCONV / 32);       // one arrival per converter warp
+            mbar_init(BAR(B_CONV + s), NCONV / 64);       // one arrival per warp of the converter group that owns the k-block
             mbar_init(BAR(B_EMPTY + s), 1);
         }
         for (int b = 0; b < NBUF; ++b) {
@@ -132,26 +132,26 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     cluster_sync_all();                                // peers' barriers exist before anyone arrives on them remotely
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == 0 || warp == 3) {
-        // ------------------------------------------------------------ W_hh tile producers (independent of h)
+    if (warp == 0) {
+        // ------------------------------------------------------------ W_hh tile producer (independent of h)
         // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
         // instruction occupies its warp for ~450 cycles (+ ~50 per extra active lane), the rows of one box are fetched
-        // one after the other (~20 cycles each), while boxes issued by different lanes / warps proceed in parallel.
-        // So: 32-row boxes, one lane per box, and two producer warps alternating k-blocks.
-        const int par = warp == 0 ? 0 : 1;
+        // one after the other (~20 cycles each), while boxes issued by different lanes proceed in parallel.
+        // So: 32-row boxes (one per gate), one lane per box, two k-blocks (six lanes) per instruction.
         int it = 0;
         for (int step = first_gemm; step < T; ++step) {
-            for (int kb = 0; kb < NKB; ++kb, ++it) {
-                if ((it & 1) != par) continue;
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
-                if (lane < 3) {
-                    if (lane == 0) GRU_TRACE_KB(0);
+            for (int kb0 = 0; kb0 < NKB; kb0 += 2) {
+                const int kb = kb0 + lane / 3, g = lane % 3;
+                if (lane < 6 && kb < NKB) {
+                    const int my = it + lane / 3, s = my % STAGES;
+                    const uint32_t ph = (my / STAGES) & 1;
+                    mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
+                    if (g == 0) GRU_TRACE_KB(0);
                     mbar_arrive_expect_tx(BAR(B_FULL_W + s), G_TILE);
-                    tma_load_2d(base + s * STAGE + A_TILE + lane * G_TILE, &tmW, k0 + kb * BK, lane * H + u0, BAR(B_FULL_W + s));
+                    tma_load_2d(base + s * STAGE + A_TILE + g * G_TILE, &tmW, k0 + kb * BK, g * H + u0, BAR(B_FULL_W + s));
                 }
                 __syncwarp();
+                it += min(2, NKB - kb0);
             }
         }
     } else if (warp == 2) {
@@ -203,15 +203,21 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 it += min(2, NKB - kb0);
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
+    } else if (warp == 1 || warp == 3) {
+        // ------------------------------------------------------------ MMA issuers (warp-uniform, one lane issues)
+        // Every warp-specialised role used to touch every k-block, so the k-block period was bounded below by the serial
+        // latency chain of ONE warp's loop body (barrier probe -> issue -> commit, ~900 cycles), not by any throughput.
+        // Two issuing warps therefore alternate accumulator chunks (the MMAs of one accumulator stay in one warp, in
+        // order), and two converter groups alternate k-blocks.
         constexpr uint32_t idesc = umma_idesc_tf32(128, NB);
+        const int par = warp == 1 ? 0 : 1;
         int it = 0, ch = 0;
         for (int step = first_gemm; step < T; ++step) {
             for (int kb = 0; kb < NKB; ++kb, ++it) {
+                const int cg = ch + kb / DRAIN_KB, buf = cg % NBUF, use = cg / NBUF;
+                if ((cg & 1) != par) continue;
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                const int cg = ch + kb / DRAIN_KB, buf = cg % NBUF, use = cg / NBUF;
                 const bool chunk_start = (kb % DRAIN_KB) == 0;
                 if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
                 if (lane == 0) GRU_TRACE_KB(2);
@@ -239,54 +245,55 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
             ch += nchunks;
         }
-    } else if (warp >= 12) {
-        // ------------------------------------------------------------ converters
-        // W: lo tile only (the raw tile is the hi operand).  h: each thread moves half of one row from shared memory
-        // into tensor memory - lanes 0-63 get the raw words (hi), lanes 64-127 the lo parts.
-        const int ct = threadIdx.x - (128 + NPROM);
-        const int quad = warp & 3, half = (warp - 12) >> 2;           // TMEM lane quadrant / which 16 of the 32 columns
-        const int arow = quad * 32 + lane;                            // A row = TMEM lane = row of the stage's A tile
+    } else if (warp >= 12 && warp < 20) {
+        // ------------------------------------------------------------ converters: two groups of 4 warps alternate k-blocks
+        // W: lo tile only (the raw tile is the hi operand).  A: each thread moves one row of the stage's [h ; h_lo] tile
+        // from shared memory into tensor memory (no arithmetic; TMEM lane = row, so a group needs all four warp quadrants).
+        const int grp = (warp - 12) >> 2;
+        const int quad = warp & 3;
+        const int gt = quad * 32 + lane;                              // thread in the group = A row = TMEM lane
         int it = 0;
         for (int step = first_gemm; step < T; ++step) {
             for (int kb = 0; kb < NKB; ++kb, ++it) {
+                if ((it & 1) != grp) continue;
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 uint8_t* st = gbase + s * STAGE;
-                const float4* w_hi = reinterpret_cast<const float4*>(st + A_TILE) + ct;
-                float4* w_lo = reinterpret_cast<float4*>(st + A_TILE + W_TILE) + ct;
-                constexpr int NW = W_TILE / 16 / NCONV;               // 3
+                const float4* w_hi = reinterpret_cast<const float4*>(st + A_TILE) + gt;
+                float4* w_lo = reinterpret_cast<float4*>(st + A_TILE + W_TILE) + gt;
+                constexpr int NW = W_TILE / 16 / 128;                 // 6
                 mbar_wait(BAR(B_FULL_W + s), ph);
-                if (ct == 0) GRU_TRACE_KB(4);
+                if (gt == 0) GRU_TRACE_KB(4);
                 float4 v[NW];
 #pragma unroll
-                for (int i = 0; i < NW; ++i) v[i] = w_hi[i * NCONV];
+                for (int i = 0; i < NW; ++i) v[i] = w_hi[i * 128];
 #pragma unroll
                 for (int i = 0; i < NW; ++i)
-                    w_lo[i * NCONV] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+                    w_lo[i * 128] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
                 mbar_wait(BAR(B_FULL_H + s), ph);
-                if (ct == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
+                if (gt == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
                 {
-                    // A row (0-63: h = hi, 64-127: h_lo written by the finalising threads of the previous step): a plain
-                    // shared-memory -> tensor-memory move, no arithmetic
-                    const float4* hrow = reinterpret_cast<const float4*>(st + arow * (BK * 4));
-                    uint32_t r[16];
+                    const float4* hrow = reinterpret_cast<const float4*>(st + gt * (BK * 4));
+                    uint32_t r[32];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float4 x = hrow[(half * 4 + c) ^ (arow & 7)];     // un-swizzle
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 x = hrow[c ^ (gt & 7)];                    // un-swizzle
                         r[4 * c] = __float_as_uint(x.x); r[4 * c + 1] = __float_as_uint(x.y);
                         r[4 * c + 2] = __float_as_uint(x.z); r[4 * c + 3] = __float_as_uint(x.w);
                     }
-                    tmem_st16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TMEM_A + s * BK + half * 16), r);
+                    const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TMEM_A + s * BK);
+                    tmem_st16(ta, r);
+                    tmem_st16(ta + 16, r + 16);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
-                if (ct == 0) GRU_TRACE_KB(6);
+                if (gt == 0) GRU_TRACE_KB(6);
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ------------------------------------------------------------ promotion + gates
         const int pt = threadIdx.x - 128;
         const int q = warp & 3;                            // TMEM lane quadrant of this warp
