@@ -39,7 +39,7 @@ constexpr int UPC = UC * KG;                // hidden units per cluster
 constexpr int NB = 3 * UPC;                 // W_hh rows per CTA (UMMA N) = 96
 constexpr int SB = 64;                      // sequences (A rows: 64 hi + 64 lo = UMMA M 128)
 constexpr int BK = 32;                      // floats per k-block = one 128-byte swizzle span
-constexpr int STAGES = 4;
+constexpr int STAGES = 5;
 constexpr int H_TILE = SB * BK * 4;         //  8 192 B raw h tile
 
 constexpr int G_TILE = UPC * BK * 4;        //  4 096 B: one gate's rows = one TMA box
@@ -56,11 +56,12 @@ constexpr int DRAIN_KB = 2;                 // k-blocks per promotion
 constexpr int NPROM = 256, NCONV = 256;
 constexpr int THREADS = 128 + NPROM + NCONV;
 constexpr int OFF_P = STAGES * STAGE;
-constexpr int OFF_BAR = OFF_P + 2 * P_FLOATS * 4;
+constexpr int OFF_BAR = OFF_P + P_FLOATS * 4;       // one partial-sum buffer (P_FREE handshake before it is rewritten)
 constexpr int SMEM = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
+static_assert(SMEM <= 232448, "shared memory budget");
 
 enum : int { B_FULL_W = 0, B_FULL_H = STAGES, B_CONV = 2 * STAGES, B_EMPTY = 3 * STAGES, B_ACC_FULL = 4 * STAGES,
-             B_ACC_EMPTY = 4 * STAGES + NBUF, B_P_READY = 4 * STAGES + 2 * NBUF, B_COUNT = 4 * STAGES + 2 * NBUF + 2 };
+             B_ACC_EMPTY = 4 * STAGES + NBUF, B_P_READY = 4 * STAGES + 2 * NBUF, B_P_FREE = 4 * STAGES + 2 * NBUF + 1, B_COUNT = 4 * STAGES + 2 * NBUF + 2 };
 static_assert(B_COUNT * 8 <= 240, "barrier area");
 constexpr int FLAG_STRIDE = 32;             // words between the step flags of consecutive CTAs (one 128-byte line each)
 static_assert(KG == 2, "flag polling reads the two step flags of a cluster");
@@ -118,8 +119,8 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             mbar_init(BAR(B_ACC_FULL + b), 1);
             mbar_init(BAR(B_ACC_EMPTY + b), NPROM / 32); // one arrival per promotion warp
         }
-        mbar_init(BAR(B_P_READY + 0), KG);
-        mbar_init(BAR(B_P_READY + 1), KG);
+        mbar_init(BAR(B_P_READY), KG);
+        mbar_init(BAR(B_P_FREE), KG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -348,8 +349,10 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 ch += nchunks;
                 if (pt == 0) GRU_TRACE_STEP(3);
                 // hi rows + lo rows -> this CTA's K-slice partial P[seq][96]
-                float* Pb = P + (gstep & 1) * P_FLOATS;
+                float* Pb = P;
                 float4* prow4 = reinterpret_cast<float4*>(Pb + prow * PLD + hf * (NB / 2));
+                // every CTA of the cluster has finished reading the previous step's partials (its own and this one's)
+                if (gstep >= 1) mbar_wait_cluster(BAR(B_P_FREE), (gstep - 1) & 1);
                 if (q >= 2) {
 #pragma unroll
                     for (int j = 0; j < NB / 8; ++j) prow4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
@@ -364,12 +367,12 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 }
                 named_bar_sync(1, NPROM);
                 // tell every CTA of the cluster (incl. this one) that this partial is complete, wait for all
-                const uint32_t pbar = BAR(B_P_READY + (gstep & 1));
+                const uint32_t pbar = BAR(B_P_READY);
                 if (pt == 0) {
 #pragma unroll
                     for (uint32_t rr = 0; rr < (uint32_t)KG; ++rr) mbar_arrive_remote_release(map_to_rank(pbar, rr));
                 }
-                mbar_wait_cluster(pbar, (gstep >> 1) & 1);
+                mbar_wait_cluster(pbar, gstep & 1);
                 if (pt == 0) GRU_TRACE_STEP(4);
                 const uint32_t pa = smem_u32(Pb + seq * PLD + ucol);
 #pragma unroll
@@ -402,7 +405,13 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             if (step < T - 1) {
                 fence_proxy_async_global();            // generic-proxy stores of h_t -> async-proxy (TMA) reads by other CTAs
                 named_bar_sync(1, NPROM);
-                if (pt == 0) st_release_gpu(flags + (size_t)blockIdx.x * FLAG_STRIDE, (unsigned)(step + 1));
+                if (pt == 0) {
+                    st_release_gpu(flags + (size_t)blockIdx.x * FLAG_STRIDE, (unsigned)(step + 1));
+                    if (step >= first_gemm) {           // the partial-sum buffers of this cluster may be rewritten
+#pragma unroll
+                        for (uint32_t rr = 0; rr < (uint32_t)KG; ++rr) mbar_arrive_remote_release(map_to_rank(BAR(B_P_FREE), rr));
+                    }
+                }
             }
             if (pt == 0) GRU_TRACE_STEP(5);
             if (TRACE && trace && pt == 0 && step == 3) trace[1024 + blockIdx.x * 2] = global_timer_ns();
