@@ -39,9 +39,9 @@ constexpr int BK = 32;
 constexpr int MAX_STAGES = 4;
 constexpr int BOX_ROWS = 32;               // rows per TMA box: the rows of a box are fetched serially, boxes in parallel
 constexpr int DRAIN_KB = 2;               // k-blocks accumulated in TMEM between promotions to FP32 registers
-constexpr int THREADS = 352;              // warp0 + warp10 TMA (even / odd k-blocks), warp1 MMA/TMEM, warps 2-5 convert, warps 6-9 promote + epilogue
-constexpr int NCONV = 128;
-constexpr int NDRAIN = 128;
+constexpr int THREADS = 640;              // 20 warps, see the kernel comment
+
+constexpr int NDRAIN = 256;
 
 template <int BN>
 struct Cfg {
@@ -49,7 +49,7 @@ struct Cfg {
     static constexpr int Q_TILE = BN * BK * 4;
     static constexpr int STAGE = P_TILE + 2 * Q_TILE;         // [P raw][Q raw = hi][Q lo]
     static constexpr int STAGES = 4;                          // 4 x 32 KB (BN 64) or 4 x 48 KB (BN 128)
-    static constexpr int STAGING = 4 * 32 * 36 * 4;
+    static constexpr int STAGING = 8 * 32 * 20 * 4;          // 8 promotion warps x (32 rows x 16 columns, row stride 20)
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM = STAGES * STAGE + STAGING + BAR_BYTES + 1024;   // +1024 alignment slack
     static constexpr int NBUF = (BN <= 64) ? 4 : 2;           // accumulator buffers (ring)
@@ -104,6 +104,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -163,6 +172,14 @@ enum : int { B_FULL = 0, B_CONV = MAX_STAGES, B_EMPTY = 2 * MAX_STAGES, B_ACC_FU
 // Persistent kernel: each CTA walks work items (p tile, q tile, k split) item = blockIdx.x + i*gridDim.x.
 // The smem stage ring and the TMEM accumulator ring run continuously across items, so the TMA / convert /
 // MMA roles work on item i+1 while the promotion warps are still storing item i.
+//
+// Warp roles (20 warps).  No role touches every k-block: the k-block period is otherwise bounded below by the serial
+// latency chain of ONE warp's loop body (barrier probe -> work -> fence -> arrive, ~1000 cycles), whatever the
+// throughput of the units behind it.
+//   0, 2   TMA producers, even / odd k-blocks (one lane per 32-row box)
+//   1, 3   MMA issuers, even / odd accumulator chunks (the MMAs of one accumulator stay in one warp, in order); 1 owns TMEM
+//   4-11   promotion + epilogue: warp -> TMEM lane quadrant (warp & 3) x column half ((warp - 4) >> 2)
+//   12-19  converters: two groups of four warps (all quadrants each), even / odd k-blocks
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
@@ -171,6 +188,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                    int tiles_q, int splits, int n_items, int mode, unsigned long long* trace) {
     using cfg = Cfg<BN>;
     constexpr int STAGES = cfg::STAGES;
+    constexpr int HN = BN / 2;                                   // accumulator columns per promotion warp
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -186,12 +204,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(BAR(B_FULL + s), (BM + BN) / BOX_ROWS);   // one arrival per 32-row TMA box
-            mbar_init(BAR(B_CONV + s), NCONV / 32);        // one arrival per converter warp
+            mbar_init(BAR(B_CONV + s), 4);                      // one arrival per warp of the converter group
             mbar_init(BAR(B_EMPTY + s), 1);
         }
         for (int b = 0; b < cfg::NBUF; ++b) {
             mbar_init(BAR(B_ACC_FULL + b), 1);
-            mbar_init(BAR(B_ACC_EMPTY + b), NDRAIN / 32);  // one arrival per promotion warp
+            mbar_init(BAR(B_ACC_EMPTY + b), NDRAIN / 32);       // one arrival per promotion warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -215,12 +233,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const int nkb = min(kb_per_split, nkb_total - kb0);
         const int nchunks = (nkb + drain_kb - 1) / drain_kb;
 
-        if (warp == 0 || warp == 10) {
+        if (warp == 0 || warp == 2) {
             // ------------------------------------------------------------ TMA producers
             // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
             // instruction occupies its warp for ~450 cycles (+ ~50 per extra active lane), the rows of one box are
-            // fetched one after the other, boxes issued by different lanes / warps proceed in parallel.  So the two
-            // tiles of a k-block are cut into 32-row boxes, one lane each, and two producer warps alternate k-blocks.
+            // fetched one after the other, boxes issued by different lanes / warps proceed in parallel.
             const int par = warp == 0 ? 0 : 1;
             constexpr int PB = BM / BOX_ROWS, QB = BN / BOX_ROWS;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -237,15 +254,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 }
                 __syncwarp();
             }
-        } else if (warp == 1) {
-            // ------------------------------------------------------------ MMA issuer
-            // The whole warp runs the loop with warp-uniform values (descriptors stay in uniform registers);
-            // one elected lane issues the tcgen05 instructions.
+        } else if (warp == 1 || warp == 3) {
+            // ------------------------------------------------------------ MMA issuers (warp-uniform loop, one lane issues)
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const int par = warp == 1 ? 0 : 1;
             for (int kb = 0; kb < nkb; ++kb) {
+                const int cg = ch + kb / drain_kb, buf = cg % cfg::NBUF, use = cg / cfg::NBUF;
+                if ((cg & 1) != par) continue;
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
-                const int cg = ch + kb / drain_kb, buf = cg % cfg::NBUF, use = cg / cfg::NBUF;
                 const bool chunk_start = (kb % drain_kb) == 0;
                 if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
                 mbar_wait(BAR(B_CONV + s), ph);
@@ -275,24 +292,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 }
                 __syncwarp();
             }
-        } else if (warp >= 2 && warp < 6) {
-            // ------------------------------------------------------------ converters: x -> (tf32 hi, lo)
-            const int ct = threadIdx.x - 64;
+        } else if (warp >= 12) {
+            // ------------------------------------------------------------ converters: FP32 -> (hi = raw word, lo)
+            const int grp = (warp - 12) >> 2;
             const int quad = warp & 3;                               // TMEM lane quadrant this warp may write
-            const int prow_t = quad * 32 + lane;                     // P tile row = TMEM lane
+            const int gt = quad * 32 + lane;                         // thread in the group = P tile row = TMEM lane
             for (int kb = 0; kb < nkb; ++kb) {
+                if (((it + kb) & 1) != grp) continue;
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 mbar_wait(BAR(B_FULL + s), ph);
-                if (trace && blockIdx.x == 0 && ct == 0 && it + kb < 64) trace[(it + kb) * 4 + 1] = clock64();
+                if (trace && blockIdx.x == 0 && gt == 0 && it + kb < 64) trace[(it + kb) * 4 + 1] = clock64();
                 uint8_t* st = gbase + s * cfg::STAGE;
                 // P: this thread's row (8 x 16 bytes, un-swizzled while reading) -> tensor memory [hi 32 | lo 32]
                 {
-                    const float4* prow = reinterpret_cast<const float4*>(st + prow_t * (BK * 4));
+                    const float4* prow = reinterpret_cast<const float4*>(st + gt * (BK * 4));
                     uint32_t r[BK];
 #pragma unroll
                     for (int c = 0; c < BK / 4; ++c) {
-                        const float4 x = prow[c ^ (prow_t & 7)];
+                        const float4 x = prow[c ^ (gt & 7)];
                         r[4 * c] = __float_as_uint(x.x); r[4 * c + 1] = __float_as_uint(x.y);
                         r[4 * c + 2] = __float_as_uint(x.z); r[4 * c + 3] = __float_as_uint(x.w);
                     }
@@ -303,40 +321,44 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     tmem_st32(ta + BK, r);
                 }
                 // Q: lo tile only (the raw tile is the hi operand)
-                constexpr int NQ = cfg::Q_TILE / 16 / NCONV;
-                const float4* q_hi = reinterpret_cast<const float4*>(st + cfg::P_TILE) + ct;
-                float4* q_lo = reinterpret_cast<float4*>(st + cfg::P_TILE + cfg::Q_TILE) + ct;
-                float4 v[NQ];
+                constexpr int NQ = cfg::Q_TILE / 16 / 128;
+                const float4* q_hi = reinterpret_cast<const float4*>(st + cfg::P_TILE) + gt;
+                float4* q_lo = reinterpret_cast<float4*>(st + cfg::P_TILE + cfg::Q_TILE) + gt;
 #pragma unroll
-                for (int i = 0; i < NQ; ++i) v[i] = q_hi[i * NCONV];
+                for (int i0 = 0; i0 < NQ; i0 += 4) {
+                    float4 v[4];
 #pragma unroll
-                for (int i = 0; i < NQ; ++i)
-                    q_lo[i * NCONV] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+                    for (int i = 0; i < 4; ++i) v[i] = q_hi[(i0 + i) * 128];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        q_lo[(i0 + i) * 128] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
             }
-        } else if (warp >= 6 && warp < 10) {
+        } else if (warp >= 4) {
             // ------------------------------------------------------------ promotion + epilogue
             // The tensor core adds into its FP32 accumulator with truncation, so error grows linearly
             // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every DRAIN_KB
             // k-blocks the TMEM partial sum is therefore added (round-to-nearest) into FP32 registers.
             const int quad = warp & 3;                              // this warp owns TMEM lanes 32*quad .. +31
-            float accr[BN];
+            const int half = (warp - 4) >> 2;                       // ... and accumulator columns half*HN .. +HN-1
+            float accr[HN];
 #pragma unroll
-            for (int j = 0; j < BN; ++j) accr[j] = 0.f;
+            for (int j = 0; j < HN; ++j) accr[j] = 0.f;
             for (int chunk = 0; chunk < nchunks; ++chunk) {
                 const int cg = ch + chunk, buf = cg % cfg::NBUF, use = cg / cfg::NBUF;
                 mbar_wait(BAR(B_ACC_FULL + buf), use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+                for (int c = 0; c < HN / 16; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * HN + c * 16), r);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) accr[c * 32 + j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; ++j) accr[c * 16 + j] += __uint_as_float(r[j]);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -345,44 +367,44 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             const int prow = p0 + quad * 32 + lane;
             const bool first_split = z == 0;
             float* Cz = C + z * split_stride;
-            float* stg = staging + quad * 32 * 36;
+            float* stg = staging + (warp - 4) * 32 * 20;
             const bool vec = !transposed && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15u) == 0) &&
                              (!(Cin && first_split) || (((ldcin & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cin) & 15u) == 0))) &&
                              (!(bias && first_split) || ((reinterpret_cast<uintptr_t>(bias) & 15u) == 0));
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < HN / 16; ++c) {
+                const int colbase = q0 + half * HN + c * 16;
                 if (transposed) {
                     // D row = output column: lanes run along the contiguous output dimension
                     if (prow < P_rows) {
                         const float bv = (bias && first_split) ? bias[prow] : 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int qrow = q0 + c * 32 + j;
+                        for (int j = 0; j < 16; ++j) {
+                            const int qrow = colbase + j;
                             if (qrow < Q_rows) {
-                                float o = accr[c * 32 + j] + bv;
+                                float o = accr[c * 16 + j] + bv;
                                 if (Cin && first_split) o += Cin[(int64_t)qrow * ldcin + prow];
                                 Cz[(int64_t)qrow * ldc + prow] = o;
                             }
                         }
                     }
                 } else {
-                    // transpose through smem (row stride 36 floats: conflict-free 16-byte accesses both ways)
+                    // transpose 32 rows x 16 columns through smem (row stride 20 floats: conflict-free 16-byte accesses)
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(stg + lane * 36 + j) =
-                            make_float4(accr[c * 32 + j], accr[c * 32 + j + 1], accr[c * 32 + j + 2], accr[c * 32 + j + 3]);
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(stg + lane * 20 + j) =
+                            make_float4(accr[c * 16 + j], accr[c * 16 + j + 1], accr[c * 16 + j + 2], accr[c * 16 + j + 3]);
                     __syncwarp();
-                    const int colbase = q0 + c * 32;
-                    if (vec && colbase + 32 <= Q_rows) {
-                        const int col = colbase + (lane & 7) * 4;
+                    if (vec && colbase + 16 <= Q_rows) {
+                        const int col = colbase + (lane & 3) * 4;
                         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (bias && first_split) bv = *reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
-                        for (int r4 = 0; r4 < 32; r4 += 4) {
-                            const int rr = r4 + (lane >> 3);
+                        for (int r8 = 0; r8 < 32; r8 += 8) {
+                            const int rr = r8 + (lane >> 2);
                             const int row = p0 + quad * 32 + rr;
                             if (row < P_rows) {
-                                float4 o = *reinterpret_cast<const float4*>(stg + rr * 36 + (lane & 7) * 4);
+                                float4 o = *reinterpret_cast<const float4*>(stg + rr * 20 + (lane & 3) * 4);
                                 o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
                                 if (Cin && first_split) {
                                     const float4 cv = *reinterpret_cast<const float4*>(Cin + (int64_t)row * ldcin + col);
@@ -392,14 +414,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                             }
                         }
                     } else {
-                        const int col = colbase + lane;
+                        const int col = colbase + (lane & 15);
                         if (col < Q_rows) {
                             const float bv = (bias && first_split) ? bias[col] : 0.f;
 #pragma unroll 4
-                            for (int rr = 0; rr < 32; ++rr) {
+                            for (int r2 = 0; r2 < 32; r2 += 2) {
+                                const int rr = r2 + (lane >> 4);
                                 const int row = p0 + quad * 32 + rr;
                                 if (row < P_rows) {
-                                    float o = stg[rr * 36 + lane] + bv;
+                                    float o = stg[rr * 20 + (lane & 15)] + bv;
                                     if (Cin && first_split) o += Cin[(int64_t)row * ldcin + col];
                                     Cz[(int64_t)row * ldc + col] = o;
                                 }
