@@ -34,6 +34,8 @@ _SIGS = {
     "gait_weak_perspective_to_translation": [P, P, I64, F32, F32, P],
     "gait_perspective_projection": [P, P, P, P, F32, F32, P, I64, I32, P],
     "gait_linear": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I64, P],
+    "gait_prepare_weight": [P, P, I64, P],
+    "gait_release_weight": [P],
     "gait_debug_linear_trace": [P],
     "gait_debug_gru_trace": [P],
     "gait_gru_workspace_bytes": [I64, I64, I64],
@@ -106,6 +108,42 @@ def call(name: str, *args):
         detail = lib.gait_last_error().decode(errors="replace")
         kind = lib.gait_error_string(rc).decode()
         raise GaitLibraryError(f"{name} failed ({rc}: {kind}): {detail}")
+
+
+_prepared = {}      # data_ptr of a registered weight -> (weakref to its owner, lo tensor, version)
+
+
+def _drop_prepared(key):
+    ent = _prepared.pop(key, None)
+    if ent is not None and _lib is not None:
+        try:
+            _lib.gait_release_weight(key)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+def prepare_weight(w: torch.Tensor) -> torch.Tensor:
+    """Register the constant FP32 CUDA weight `w` (contiguous; a Parameter, buffer or packed tensor that its owner keeps
+    alive) with the library: its TF32 lo part is computed once and the GEMMs that use `w` (or a view into it) load it by TMA
+    instead of recomputing it per call.  Idempotent; re-prepared when `w` was modified in place; released when `w` is
+    garbage-collected."""
+    import weakref
+    if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+        raise GaitLibraryError("prepare_weight: expected a contiguous float32 CUDA tensor")
+    key = w.data_ptr()
+    hit = _prepared.get(key)
+    if hit is not None and hit[0]() is w and hit[2] == w._version:
+        return w
+    if hit is not None:
+        _drop_prepared(key)
+    lo = torch.empty(w.shape, device=w.device, dtype=torch.float32)
+    call("gait_prepare_weight", key, ptr(lo), w.numel(), stream_ptr())
+    _prepared[key] = (weakref.ref(w, lambda _r, k=key: _drop_prepared(k)), lo, w._version)
+    return w
+
+
+def release_weight(w: torch.Tensor):
+    _drop_prepared(w.data_ptr())
 
 
 def launch_count() -> int:

@@ -29,6 +29,9 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace gait {
@@ -180,10 +183,13 @@ enum : int { B_FULL = 0, B_CONV = MAX_STAGES, B_EMPTY = 2 * MAX_STAGES, B_ACC_FU
 //   1, 3   MMA issuers, even / odd accumulator chunks (the MMAs of one accumulator stay in one warp, in order); 1 owns TMEM
 //   4-11   promotion + epilogue: warp -> TMEM lane quadrant (warp & 3) x column half ((warp - 4) >> 2)
 //   12-19  converters: two groups of four warps (all quadrants each), even / odd k-blocks
-template <int BN>
+//
+// QLO = true: the lo parts of the BN-row operand (constant weights) were split off once (gait_prepare_weight); they are
+// loaded by TMA next to the raw tile and the converters only handle the 128-row operand.
+template <int BN, bool QLO>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
-                   const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
+                   const __grid_constant__ CUtensorMap tmQlo, const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
                    int P_rows, int Q_rows, int K, int transposed, int kb_per_split, int64_t split_stride,
                    int tiles_q, int splits, int n_items, int mode, unsigned long long* trace) {
     using cfg = Cfg<BN>;
@@ -203,7 +209,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(BAR(B_FULL + s), (BM + BN) / BOX_ROWS);   // one arrival per 32-row TMA box
+            mbar_init(BAR(B_FULL + s), (BM + (QLO ? 2 : 1) * BN) / BOX_ROWS);   // one arrival per 32-row TMA box
             mbar_init(BAR(B_CONV + s), 4);                      // one arrival per warp of the converter group
             mbar_init(BAR(B_EMPTY + s), 1);
         }
@@ -246,11 +252,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
                 const uint32_t st = base + s * cfg::STAGE;
-                if (lane < PB + QB) {
+                if (lane < PB + (QLO ? 2 : 1) * QB) {
                     if (trace && blockIdx.x == 0 && lane == 0 && it + kb < 64) trace[(it + kb) * 4 + 0] = clock64();
                     mbar_arrive_expect_tx(BAR(B_FULL + s), BOX_ROWS * BK * 4);
                     if (lane < PB) tma_load_2d(st + lane * (BOX_ROWS * BK * 4), &tmP, (kb0 + kb) * BK, p0 + lane * BOX_ROWS, BAR(B_FULL + s));
-                    else tma_load_2d(st + cfg::P_TILE + (lane - PB) * (BOX_ROWS * BK * 4), &tmQ, (kb0 + kb) * BK, q0 + (lane - PB) * BOX_ROWS, BAR(B_FULL + s));
+                    else if (lane < PB + QB) tma_load_2d(st + cfg::P_TILE + (lane - PB) * (BOX_ROWS * BK * 4), &tmQ, (kb0 + kb) * BK, q0 + (lane - PB) * BOX_ROWS, BAR(B_FULL + s));
+                    else tma_load_2d(st + cfg::P_TILE + cfg::Q_TILE + (lane - PB - QB) * (BOX_ROWS * BK * 4), &tmQlo, (kb0 + kb) * BK, q0 + (lane - PB - QB) * BOX_ROWS, BAR(B_FULL + s));
                 }
                 __syncwarp();
             }
@@ -320,8 +327,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     for (int j = 0; j < BK; ++j) r[j] = __float_as_uint(tf32_lo(__uint_as_float(r[j])));
                     tmem_st32(ta + BK, r);
                 }
-                // Q: lo tile only (the raw tile is the hi operand)
-                constexpr int NQ = cfg::Q_TILE / 16 / 128;
+                // Q: lo tile only (the raw tile is the hi operand); nothing to do for prepared weights
+                constexpr int NQ = QLO ? 0 : cfg::Q_TILE / 16 / 128;
                 const float4* q_hi = reinterpret_cast<const float4*>(st + cfg::P_TILE) + gt;
                 float4* q_lo = reinterpret_cast<float4*>(st + cfg::P_TILE + cfg::Q_TILE) + gt;
 #pragma unroll
@@ -335,7 +342,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (!QLO) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
             }
@@ -452,14 +459,14 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t K, i
 
 unsigned long long* g_trace = nullptr;
 
-template <int BN>
-static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const float* bias, const float* Cin, int64_t ldcin,
-                  float* C, int64_t ldc, int P_rows, int Q_rows, int K, int transposed, int splits, int64_t split_stride,
-                  cudaStream_t stream) {
+template <int BN, bool QLO>
+static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap& tmQlo, const float* bias, const float* Cin,
+                  int64_t ldcin, float* C, int64_t ldc, int P_rows, int Q_rows, int K, int transposed, int splits,
+                  int64_t split_stride, cudaStream_t stream) {
     using cfg = Cfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        GAIT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
+        GAIT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, QLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
         attr_set = true;
     }
     const int nkb = (K + BK - 1) / BK;
@@ -485,9 +492,9 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const float* b
         const char* e = getenv("GAITB200_TC_MODE");
         mode = e ? atoi(e) : 0;
     }
-    gemm_tf32x3_kernel<BN><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
-                                                                transposed, kb_per_split, split_stride, tiles_q, splits,
-                                                                n_items, mode, g_trace);
+    gemm_tf32x3_kernel<BN, QLO><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
+                                                                     transposed, kb_per_split, split_stride, tiles_q, splits,
+                                                                     n_items, mode, g_trace);
     return check_launch("linear(tf32x3 tcgen05)");
 }
 
@@ -501,12 +508,32 @@ bool linear_tc_eligible(const float* A, int64_t lda, const float* W, int64_t ldw
            (M >= 16 || N >= 512);
 }
 
+// ---- prepared weights: lo parts split off once per model (gait_prepare_weight) --------------------------------------------
+namespace {
+struct PreparedWeight { const float* base; const float* lo; int64_t n; };
+std::mutex g_prep_mutex;
+std::vector<PreparedWeight> g_prepared;
+}  // namespace
+
+// lo pointer matching W (which may point inside a registered array), or nullptr
+static const float* find_prepared_lo(const float* W, int64_t n_needed) {
+    std::lock_guard<std::mutex> lock(g_prep_mutex);
+    for (const auto& e : g_prepared)
+        if (W >= e.base && W + n_needed <= e.base + e.n) return e.lo + (W - e.base);
+    return nullptr;
+}
+
+__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) lo[i] = tc::tf32_lo(x[i]);
+}
+
 // splits > 1: C must hold `splits` partial results `split_stride` floats apart; bias/Cin go into split 0.
 int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* Cin,
                      int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int splits,
                      int64_t split_stride, cudaStream_t stream) {
     using namespace tc;
-    CUtensorMap tmP, tmQ;
+    CUtensorMap tmP, tmQ, tmQlo;
     // few activation rows: put the weight rows on the 128 TMEM lanes, activations on the N side
     const bool transposed = M <= 64 || (M < 128 && N >= 128);
     if (transposed) {
@@ -514,15 +541,45 @@ int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, c
         GAIT_TRY(make_map(&tmP, W, N, K, ldw, BM));
         GAIT_TRY(make_map(&tmQ, A, M, K, lda, bn));
         if (bn == 64)
-            return launch<64>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
-        return launch<128>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
+            return launch<64, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
+        return launch<128, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
     }
     const int bn = (ceil_div(M, BM) * ceil_div(N, 128) < 120 && N > 64) ? 64 : 128;
     GAIT_TRY(make_map(&tmP, A, M, K, lda, BM));
     GAIT_TRY(make_map(&tmQ, W, N, K, ldw, bn));
+    const float* Wlo = find_prepared_lo(W, (N - 1) * ldw + K);
+    if (Wlo && aligned16(Wlo)) {
+        GAIT_TRY(make_map(&tmQlo, Wlo, N, K, ldw, bn));
+        if (bn == 64)
+            return launch<64, true>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
+        return launch<128, true>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
+    }
     if (bn == 64)
-        return launch<64>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
-    return launch<128>(tmP, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
+        return launch<64, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
+    return launch<128, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
 }
 
 }  // namespace gait
+
+extern "C" {
+
+int gait_prepare_weight(const float* W, float* W_lo, int64_t n, gait_stream_t stream) {
+    GAIT_REQUIRE(n >= 0 && (n == 0 || (W && W_lo)), "prepare_weight: null pointer or negative size");
+    if (n == 0) return GAIT_OK;
+    gait::split_lo_kernel<<<(unsigned)gait::ceil_div(n, 256), 256, 0, gait::as_stream(stream)>>>(W, W_lo, n);
+    GAIT_TRY(gait::check_launch("prepare_weight"));
+    std::lock_guard<std::mutex> lock(gait::g_prep_mutex);
+    for (auto& e : gait::g_prepared)
+        if (e.base == W) { e.lo = W_lo; e.n = n; return GAIT_OK; }
+    gait::g_prepared.push_back({W, W_lo, n});
+    return GAIT_OK;
+}
+
+int gait_release_weight(const float* W) {
+    std::lock_guard<std::mutex> lock(gait::g_prep_mutex);
+    for (size_t i = 0; i < gait::g_prepared.size(); ++i)
+        if (gait::g_prepared[i].base == W) { gait::g_prepared.erase(gait::g_prepared.begin() + i); return GAIT_OK; }
+    return GAIT_OK;
+}
+
+}  // extern "C"

@@ -133,6 +133,7 @@ class GaitHead(nn.Module):
         ptr, call, st = L.ptr, L.call, L.stream_ptr
         state = p["state"].data_ptr()
         betas, cam = state + 4 * 144, state + 4 * 154
+        L.prepare_weight(gru.weight_ih_l0)
         return [
             ("gru", lambda: call(
                 "gait_gru_layer", ptr(p["x"]), H, ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), ptr(gru.bias_ih_l0),

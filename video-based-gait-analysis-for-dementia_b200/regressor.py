@@ -82,6 +82,8 @@ class Regressor(nn.Module):
                 "bd": torch.cat([self.decpose.bias, self.decshape.bias, self.deccam.bias], 0).detach().float().contiguous(),
                 "init": init,
             }
+        for name in ("W1x", "W1s", "W2", "Wd"):      # constant GEMM weights: TF32 lo parts split off once
+            L.prepare_weight(self._packed[name])
         self._packed_key = key
         return self._packed
 

@@ -181,6 +181,7 @@ class SMPL(nn.Module):
             "map_spin": i32(int(j) for j in self.joint_map),
             "map_smplx": i32(range(NUM_JOINTS + n_lm)),
         }
+        L.prepare_weight(self._packed["basis_t"])   # constant blend-GEMM operand: TF32 lo part split off once
         self._packed_key = key
         return self._packed
 

@@ -35,7 +35,10 @@ def gru_forward(gru: nn.GRU, x: torch.Tensor, resid: torch.Tensor | None = None,
         last = layer == gru.num_layers - 1
         for d in range(dirs):
             sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
-            w_ih = L.f32(getattr(gru, "weight_ih" + sfx).detach(), "weight_ih")
+            w_ih_p = getattr(gru, "weight_ih" + sfx)
+            if not gru.training and w_ih_p.is_contiguous():
+                L.prepare_weight(w_ih_p)                      # input-projection weights: TF32 lo part split off once
+            w_ih = L.f32(w_ih_p.detach(), "weight_ih")
             w_hh = L.f32(getattr(gru, "weight_hh" + sfx).detach(), "weight_hh")
             if gru.bias:
                 b_ih = L.f32(getattr(gru, "bias_ih" + sfx).detach(), "bias_ih")
