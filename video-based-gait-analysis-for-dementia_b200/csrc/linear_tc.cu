@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const __grid_constant__ CUtensorMap tmQlo, const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
                    int P_rows, int Q_rows, int K, int transposed, int kb_per_split, int64_t split_stride,
-                   int tiles_q, int splits, int n_items, int mode, unsigned long long* trace) {
+                   int tiles_p, int splits, int n_items, int mode, unsigned long long* trace) {
     using cfg = Cfg<BN>;
     constexpr int STAGES = cfg::STAGES;
     constexpr int HN = BN / 2;                                   // accumulator columns per promotion warp
@@ -231,9 +231,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     int it = 0;        // k-blocks processed so far by this CTA (position in the stage ring)
     int ch = 0;        // accumulator chunks processed so far (position in the TMEM ring)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        // item order: k-split fastest, then the 128-row tiles, then the BN-row (weight) tiles - CTAs that run concurrently
+        // share weight tiles, so a large weight matrix is streamed from HBM once instead of once per 128-row tile
         const int z = item % splits;
-        const int qt = (item / splits) % tiles_q;
-        const int pt = item / (splits * tiles_q);
+        const int pt = (item / splits) % tiles_p;
+        const int qt = item / (splits * tiles_p);
         const int p0 = pt * BM, q0 = qt * BN;
         const int kb0 = z * kb_per_split;
         const int nkb = min(kb_per_split, nkb_total - kb0);
@@ -493,7 +495,7 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
         mode = e ? atoi(e) : 0;
     }
     gemm_tf32x3_kernel<BN, QLO><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
-                                                                     transposed, kb_per_split, split_stride, tiles_q, splits,
+                                                                     transposed, kb_per_split, split_stride, tiles_p, splits,
                                                                      n_items, mode, g_trace);
     return check_launch("linear(tf32x3 tcgen05)");
 }
