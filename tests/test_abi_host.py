@@ -79,6 +79,44 @@ def test_argument_validation_without_gpu(lib):
     assert lib.gait_launch_count() == n0
 
 
+def test_new_entry_points_validate_without_gpu(lib):
+    """joints-only skinning, post-processing, heads and prepared weights: empty problems succeed, bad arguments fail, no launch."""
+    n0 = lib.gait_launch_count()
+    assert lib.gait_smpl_lbs_tc_joints(None, 0, None, None, None, None, None, 21, None, 0, 6890, None) == 0
+    assert lib.gait_smpl_lbs_tc_joints(C.c_void_p(16), 20736, C.c_void_p(16), C.c_void_p(16), None, None, None, 0, None, 4, 6890, None) == -1
+    assert lib.gait_one_euro_filter(None, None, 0, 72, 0.004, 0.7, 1.0, None) == 0
+    assert lib.gait_one_euro_filter(None, None, 4, 72, 0.004, 0.7, 1.0, None) == -1
+    assert lib.gait_crop_cam_to_orig_img(None, None, 1, 4, 1280.0, 720.0, None, 0, None) == 0
+    assert lib.gait_crop_cam_to_orig_img(C.c_void_p(16), C.c_void_p(16), 1, 2, 1280.0, 720.0, C.c_void_p(16), 3, None) == -1
+    assert lib.gait_crop_coords_to_orig_img(C.c_void_p(16), 1, 4, C.c_void_p(16), C.c_void_p(16), 3, 25, 1, 224.0, None) == -1
+    assert lib.gait_keypoint_attention(None, None, 1.0, None, 0, 128, 24, 3136, 1, 1, 1, None) == 0
+    assert lib.gait_keypoint_attention(C.c_void_p(16), C.c_void_p(16), 1.0, C.c_void_p(16), 2, 128, 24, 1 << 20, 1, 1, 1, None) == -1
+    assert lib.gait_locally_connected(C.c_void_p(16), 1, 1, 1, C.c_void_p(16), 1, 1, 1, None, 0, 0, C.c_void_p(16), 1, 1, 1,
+                                      C.c_void_p(16), None, 2, 3, 4, 24, None) == -1          # resid without out2
+    assert lib.gait_activation(C.c_void_p(16), C.c_void_p(16), 8, 7, 0.0, None) == -1
+    assert lib.gait_prepare_weight(None, None, 0, None) == 0 and lib.gait_prepare_weight(None, None, 5, None) == -1
+    assert lib.gait_release_weight(C.c_void_p(16)) == 0
+    assert lib.gait_launch_count() == n0
+
+
+def test_postproc_and_heads_have_no_cpu_path():
+    """Without a CUDA device the new host modules raise instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    from gaitb200 import postproc as PP
+    from gaitb200.layers import KeypointAttention, LocallyConnected2d
+    with pytest.raises(_lib.GaitLibraryError):
+        PP.one_euro_filter(np.zeros((4, 72), np.float32))
+    with pytest.raises(_lib.GaitLibraryError):
+        PP.convert_crop_cam_to_orig_img(np.zeros((2, 3), np.float32), np.ones((2, 4)), 640, 480)
+    with pytest.raises(TypeError):
+        PP.one_euro_filter(np.zeros((4, 72), np.float64))
+    with pytest.raises(_lib.GaitLibraryError):
+        KeypointAttention()(torch.zeros(1, 8, 4, 4), torch.zeros(1, 24, 4, 4))
+    with pytest.raises(_lib.GaitLibraryError):
+        LocallyConnected2d(3, 4, [24, 1], 1, 1)(torch.zeros(1, 3, 24, 1))
+
+
 def test_product_has_no_cpu_path(smpl_data):
     from gaitb200 import geometry as G
     with pytest.raises(_lib.GaitLibraryError):
