@@ -59,6 +59,7 @@ def parse_args():
                     help="synthetic SMPL weights: SMPL-like sparse (<=4 skin weights / vertex) or fully dense")
     ap.add_argument("--joints-only", action="store_true",
                     help="BASELINE config 5: Kinect-25 joints without mesh write-back (the skinned mesh never leaves the SMs)")
+    ap.add_argument("--slots", type=int, default=2, help="buffer sets for the pipelined end-to-end path")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gather", choices=["none", "joints", "mesh"], default="none",
                     help="NCCL all-gather of Kinect-25 joints (or joints+mesh) inside the timed step (N>1)")
@@ -228,12 +229,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     feats_host = synthetic.make_features(S, T, seed=1234 + rank).pin_memory()
 
     if args.no_graph:
-        head.plan(S, T, slots=2)
+        head.plan(S, T, slots=args.slots)
         n0 = _lib.launch_count()
         head.step()
         launches_per_step = _lib.launch_count() - n0
     else:
-        head.capture(S, T, slots=2)
+        head.capture(S, T, slots=args.slots)
         launches_per_step = head.launches_per_step
     head.input.copy_(feats_host, non_blocking=True)
     torch.cuda.synchronize()
@@ -284,13 +285,13 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # ---- end to end through the public API: pinned host features -> H2D -> step -> D2H of every output.
     # GaitHead.run_host_batches overlaps copy-in / kernels / copy-out of consecutive batches (two buffer slots).
     outs = head.outputs()
-    host_outs = [head.alloc_host_outputs() for _ in range(2)]
+    host_outs = [head.alloc_host_outputs() for _ in range(args.slots)]
     feats_hosts = [feats_host, feats_host.clone().pin_memory()]
     h2d = feats_host.numel() * 4
     d2h = sum(v.numel() * 4 for v in host_outs[0].values())
     e2e_steps = max(24, args.steps // 2)
     ins = [feats_hosts[i % 2] for i in range(e2e_steps)]
-    hos = [host_outs[i % 2] for i in range(e2e_steps)]
+    hos = [host_outs[i % args.slots] for i in range(e2e_steps)]
     head.run_host_batches(ins[:4], hos[:4])                    # warm-up
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,7 +305,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     e2e_ms = float(te.item()) / e2e_steps
     e2e_value = F * world / (e2e_ms / 1e3)
     ck = "kinect25" if args.joints_only else "verts"
-    e2e_check = float((host_outs[(e2e_steps - 1) % 2][ck] - head.outputs((e2e_steps - 1) % 2)[ck].cpu()).abs().max())
+    e2e_check = float((host_outs[(e2e_steps - 1) % args.slots][ck] - head.outputs((e2e_steps - 1) % args.slots)[ck].cpu()).abs().max())
 
     if rank != 0:
         return
@@ -359,7 +360,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "d2h_gbs": d2h / (e2e_ms * 1e-3) / 1e9,
                 "host_vs_device_max_abs_diff": e2e_check,
                 "note": "GaitHead.run_host_batches: copy-in / kernels / copy-out of consecutive batches overlap on 3 streams; "
-                        "D2H = mesh + one packed buffer of the small outputs; PCIe D2H measured ceiling on this box ~57 GB/s"},
+                        "D2H = one transfer of the packed output buffer [mesh | small outputs]; PCIe D2H measured ceiling on this box ~57 GB/s"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": roofline,

@@ -39,8 +39,8 @@ def _small_layout(F: int):
 
 
 class HostOutputs(dict):
-    """dict of pinned host tensors from GaitHead.alloc_host_outputs(); `.packed_small` is the buffer behind the small ones."""
-    packed_small = None
+    """dict of pinned host tensors from GaitHead.alloc_host_outputs(); `.packed` is the single buffer behind all of them."""
+    packed = None
 
 
 class GaitHead(nn.Module):
@@ -85,17 +85,25 @@ class GaitHead(nn.Module):
             "aop": e(lib.gait_smpl_lbs_aop_bytes(F) // 4),
             "coef": e(F, 224), "v_posed": e(F, 384 * ((V + 127) // 128)),
             # full mesh (F,V,3), or in joints-only mode just the landmark vertices the joint sets read (config 5)
-            "verts": e(F, V, 3) if self.write_mesh else None,
+            "verts": None,
             "lm_verts": None if self.write_mesh else e(F, self.regressor.smpl._prepare()["n_landmarks"], 3),
             "lm_iota": None if self.write_mesh else torch.arange(self.regressor.smpl._prepare()["n_landmarks"], dtype=torch.int32, device=dev),
             "extra": e((V + 127) // 128, F, 1, 3),
-            # the small per-frame outputs live in ONE buffer, so the host copy of a step is two transfers (mesh + this)
-            "small": e(_small_layout(F)[1]),
+            # every output of a step lives in ONE buffer [mesh | small per-frame outputs], so the host copy is one transfer
+            "outbuf": e(self._mesh_floats(F, V) + _small_layout(F)[1]),
             "gather": torch.tensor(SPIN2_TO_KINECTV2, dtype=torch.int32, device=dev),
         }
+        nm = self._mesh_floats(F, V)
+        if self.write_mesh:
+            p["verts"] = p["outbuf"][:F * V * 3].view(F, V, 3)
+        p["small"] = p["outbuf"][nm:]
         for key, _, shape, off, n in _small_layout(F)[0]:
             p[key] = p["small"][off:off + n].view(F, *shape)
         return p
+
+    def _mesh_floats(self, F, V):
+        """floats reserved for the mesh at the front of the output buffer (16-byte multiple; 0 in joints-only mode)"""
+        return (F * V * 3 + 3) // 4 * 4 if self.write_mesh else 0
 
     def alloc_host_outputs(self):
         """Pinned host buffers for run_host_batches: a dict with the keys/shapes of outputs(); the small outputs are views of
@@ -103,13 +111,15 @@ class GaitHead(nn.Module):
         p = self._plan
         S, T, F = p["S"], p["T"], p["F"]
         layout, total = _small_layout(F)
-        small = torch.empty(total).pin_memory()
+        nm = self._mesh_floats(F, p["V"])
+        buf = torch.empty(nm + total).pin_memory()
         out = HostOutputs()
-        out.packed_small = small
+        out.packed = buf
+        small = buf[nm:]
         for _, name, shape, off, n in layout:
             out[name] = small[off:off + n].view(S, T, *shape)
         if self.write_mesh:
-            out["verts"] = torch.empty(S, T, p["V"], 3).pin_memory()
+            out["verts"] = buf[:F * p["V"] * 3].view(S, T, p["V"], 3)
         return out
 
     def plan(self, S: int, T: int, slots: int = 1):
@@ -277,9 +287,7 @@ class GaitHead(nn.Module):
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp[k])
                 if isinstance(out_host, HostOutputs):
-                    if self.write_mesh:
-                        out_host["verts"].copy_(self.outputs(k)["verts"], non_blocking=True)
-                    out_host.packed_small.copy_(p["small"], non_blocking=True)
+                    out_host.packed.copy_(p["outbuf"], non_blocking=True)
                 else:
                     for key, v in self.outputs(k).items():
                         out_host[key].copy_(v, non_blocking=True)
