@@ -118,6 +118,27 @@ def test_linear_vs_torch_fp32(M, N, K, lib_loaded):
     assert maxerr(Cd, (A.double() @ W.double().T + Cin.double()).float()) <= 2e-5 * max(1.0, K ** 0.5 / 8)
 
 
+def test_prepared_weight_is_bit_identical(lib_loaded):
+    """gait_prepare_weight only moves the lo-part computation out of the kernel: same bits with and without it, also for a
+    view into the registered array; releasing restores the in-kernel path."""
+    L = lib_loaded
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 300, 320, 256
+    A = torch.randn(M, K, generator=g).cuda()
+    Wbig = (torch.randn(2 * N, K, generator=g) / K ** 0.5).cuda()
+    W = Wbig[N:]                                              # a view into the second half
+    out0, out1, out2 = (torch.empty(M, N, device="cuda") for _ in range(3))
+    run = lambda o: L.call("gait_linear", A.data_ptr(), K, W.data_ptr(), K, None, None, 0, o.data_ptr(), N, M, N, K, L.stream_ptr())
+    run(out0)
+    L.prepare_weight(Wbig)
+    run(out1)
+    L.release_weight(Wbig)
+    run(out2)
+    torch.cuda.synchronize()
+    assert torch.equal(out0, out1) and torch.equal(out0, out2)
+    assert maxerr(out0, (A.double() @ W.double().T).float()) <= 2e-5
+
+
 @pytest.mark.parametrize("cfg", [
     dict(S=2, T=5, I=32, H=32, layers=1, bi=False),
     dict(S=3, T=7, I=48, H=20, layers=2, bi=True),            # ragged sizes, not multiples of 4 per gate
