@@ -148,7 +148,8 @@ def test_prepared_weight_is_bit_identical(lib_loaded):
     dict(S=5, T=9, I=96, H=256, layers=2, bi=True),           # persistent kernel: ragged S, reverse direction, ldy = 2H
     dict(S=64, T=4, I=40, H=64, layers=1, bi=False),          # persistent kernel: one k-block per CTA
     dict(S=37, T=1, I=64, H=128, layers=1, bi=False),         # single step: no recurrent GEMM at all
-    dict(S=70, T=5, I=64, H=128, layers=1, bi=False),         # S > 64: per-step path
+    dict(S=70, T=5, I=64, H=128, layers=1, bi=False),         # 64 < S <= 192: two launches of the persistent kernel (64 + 6 sequences)
+    dict(S=200, T=3, I=64, H=128, layers=1, bi=False),        # S > 192: per-step path
 ])
 def test_gru_vs_torch(cfg, lib_loaded):
     from gaitb200.temporal import gru_forward

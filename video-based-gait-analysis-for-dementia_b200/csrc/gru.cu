@@ -100,11 +100,21 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
         gru_path = e ? atoi(e) : 0;
     }
     if (gru_path != 1 && linear_path() != 1) {
-        if (gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S, T, H)) {
+        // up to 192 sequences run as consecutive 64-sequence launches of the persistent kernel (beyond that the per-step
+        // GEMMs, whose efficiency grows with the number of rows, win; measured with scripts/stage_sweep.py)
+        constexpr int64_t kChunk = 64, kMaxChunked = 192;
+        const int64_t S0 = std::min<int64_t>(S, kChunk);
+        if (S <= kMaxChunked && gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S0, T, H)) {
             unsigned int* counter = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);
             uintptr_t lo_addr = (reinterpret_cast<uintptr_t>(counter) + 128 * (size_t)(H / 16 + 1) + 127) & ~(uintptr_t)127;
-            return gru_recurrent_launch(gi, W_hh, b_hh, h0, y, ldy, resid, ldres, out, ldout, hn, S, T, H, reverse, counter,
-                                        reinterpret_cast<float*>(lo_addr), st);
+            for (int64_t s0 = 0; s0 < S; s0 += kChunk) {
+                const int64_t Sc = std::min<int64_t>(kChunk, S - s0);
+                GAIT_TRY(gru_recurrent_launch(gi + s0 * T * 3 * H, W_hh, b_hh, h0 ? h0 + s0 * H : nullptr, y + s0 * T * ldy, ldy,
+                                              resid ? resid + s0 * T * ldres : nullptr, ldres, out ? out + s0 * T * ldout : nullptr,
+                                              ldout, hn ? hn + s0 * H : nullptr, Sc, T, H, reverse, counter,
+                                              reinterpret_cast<float*>(lo_addr), st));
+            }
+            return GAIT_OK;
         }
         if (gru_path == 2) {
             set_error("gru_layer: persistent recurrent kernel not eligible for S=%lld T=%lld H=%lld", (long long)S, (long long)T, (long long)H);
