@@ -313,7 +313,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     stages = head.profile_stages(iters=10, flush=flush_l2)
     # dominant HBM kernel: average launch duration over 8 consecutive launches between one event pair, alternating
     # two buffer sets (2 x 170 MB > L2); the single-launch figure (own event pair after an L2 flush) is kept beside it
-    lbs_ms = head.time_stage_back_to_back("lbs", launches=8, repeats=5)
+    lbs_ms = head.time_stage_back_to_back("lbs", launches=8, repeats=5) if args.slots >= 2 else stages["lbs"]["ms"]
     lbs_bytes = F * (LBS_BYTES_PER_FRAME - (6890 * 3 * 4 - 21 * 12 if args.joints_only else 0)) + LBS_BYTES_ONCE
     lbs_gbs = lbs_bytes / (lbs_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
@@ -325,8 +325,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     roofline = {"kernel": "smpl_lbs_tc_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": lbs_bytes, "kernel_ms": lbs_ms,
-                "timing": "8 consecutive launches between one CUDA-event pair on the launching stream, two alternating "
-                          "buffer sets (340 MB > 126 MB L2), best of 5",
+                "timing": ("8 consecutive launches between one CUDA-event pair on the launching stream, two alternating "
+                           "buffer sets (340 MB > 126 MB L2), best of 5") if args.slots >= 2 else
+                          "one launch per CUDA-event pair after an L2 flush (--slots 1)",
                 "kernel_ms_single_launch_event_pair": stages["lbs"]["ms"],
                 "frac_single_launch_event_pair": lbs_bytes / (stages["lbs"]["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     stage_report = {}
