@@ -150,6 +150,14 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
 int gait_smpl_pose_chain(const float* R, const float* betas, int64_t ldb, const float* J_template,
                          const float* J_shapedirs, const int32_t* parents, float* A, float* J_posed,
                          float* coef, float* Aop, int64_t F, gait_stream_t stream);
+/* The same kernel with the 6-D -> rotation conversion (geometry.py:395-410, eps) in front and theta packing (spin.py:288,
+ * pare.py:79: [cam | axis-angle(72) | betas], geometry.py:68-97 route) behind it, so the head needs one launch where
+ * gait_rot6d_to_rotmat + gait_smpl_pose_chain + gait_pack_theta need three.  x6: row f at x6 + f*ldx6 holds the 24
+ * interleaved 6-vectors; R_out (F,24,3,3) receives the rotations; theta (F,85) optional (needs cam (F,3), stride ldcam). */
+int gait_smpl_pose_chain_rot6d(const float* x6, int64_t ldx6, float eps, const float* betas, int64_t ldb, const float* cam,
+                               int64_t ldcam, const float* J_template, const float* J_shapedirs, const int32_t* parents,
+                               float* R_out, float* A, float* J_posed, float* coef, float* Aop, float* theta, int64_t F,
+                               gait_stream_t stream);
 /* Blend shapes (smplx lbs.blend_shapes + pose offsets): v_posed (F,3V) = coef (F,224) . basis_t^T,
  * basis_t (3V,224) = [posedirs^T | shapedirs | v_template | 0]; v_posed row stride ldv >= 3V. */
 int gait_smpl_blend(const float* coef, const float* basis_t, float* v_posed, int64_t ldv, int64_t F, int64_t V3,

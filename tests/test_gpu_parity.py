@@ -456,6 +456,36 @@ def test_head_graph_replay_dense_variant(lib_loaded):
         _check_head(head.outputs(), oracle(feats))
 
 
+def test_fused_chain_entry_is_bit_identical(smpl_data, lib_loaded):
+    """gait_smpl_pose_chain_rot6d == gait_rot6d_to_rotmat + gait_smpl_pose_chain + gait_pack_theta, bit for bit."""
+    from gaitb200.smpl import SMPL
+    L = lib_loaded
+    F = 37
+    pk = SMPL(smpl_data).cuda()._prepare()
+    g = torch.Generator().manual_seed(4)
+    state = torch.zeros(F, 160)
+    state[:, :144] = torch.tensor([1., 0, 0, 1, 0, 0]).repeat(24) + 0.4 * torch.randn(F, 144, generator=g)
+    state[:, 144:154] = torch.randn(F, 10, generator=g)
+    state[:, 154:157] = torch.tensor([0.9, 0.05, -0.02]) + 0.1 * torch.randn(F, 3, generator=g)
+    state = state.cuda()
+    sp = state.data_ptr()
+    e = lambda *sh: torch.empty(*sh, device="cuda")
+    aop_n = L.load().gait_smpl_lbs_aop_bytes(F) // 4
+    R1, Jp1, cf1, ao1, th1 = e(F, 24, 3, 3), e(F, 24, 3), e(F, 224), torch.zeros(aop_n, device="cuda"), e(F, 85)
+    R2, Jp2, cf2, ao2, th2 = e(F, 24, 3, 3), e(F, 24, 3), e(F, 224), torch.zeros(aop_n, device="cuda"), e(F, 85)
+    st = L.stream_ptr()
+    L.call("gait_rot6d_to_rotmat", sp, 24, 160, R1.data_ptr(), F * 24, 1e-6, st)
+    L.call("gait_smpl_pose_chain", R1.data_ptr(), sp + 4 * 144, 160, L.ptr(pk["J_template"]), L.ptr(pk["J_shapedirs"]),
+           L.ptr(pk["parents"]), None, Jp1.data_ptr(), cf1.data_ptr(), ao1.data_ptr(), F, st)
+    L.call("gait_pack_theta", R1.data_ptr(), sp + 4 * 154, 160, sp + 4 * 144, 160, th1.data_ptr(), F, st)
+    L.call("gait_smpl_pose_chain_rot6d", sp, 160, 1e-6, sp + 4 * 144, 160, sp + 4 * 154, 160, L.ptr(pk["J_template"]),
+           L.ptr(pk["J_shapedirs"]), L.ptr(pk["parents"]), R2.data_ptr(), None, Jp2.data_ptr(), cf2.data_ptr(), ao2.data_ptr(),
+           th2.data_ptr(), F, st)
+    torch.cuda.synchronize()
+    for a, b in ((R1, R2), (Jp1, Jp2), (cf1, cf2), (ao1, ao2), (th1, th2)):
+        assert torch.equal(a, b)
+
+
 def test_head_joints_only_c5(lib_loaded):
     """BASELINE config 5: the joints-only path (mesh never written to HBM) gives bit-identical joints, Kinect-25
     joints, kp_2d and theta to the full-mesh path on the same inputs, and agrees with the oracle."""

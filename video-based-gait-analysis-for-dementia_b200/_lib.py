@@ -44,6 +44,7 @@ _SIGS = {
     "gait_hmr_workspace_bytes": [I64, I64],
     "gait_hmr_regressor": [P, I64, P, P, P, P, P, P, P, P, I64, I32, P, I64, I64, I64, P, SZ, P],
     "gait_smpl_pose_chain": [P, P, I64, P, P, P, P, P, P, P, I64, P],
+    "gait_smpl_pose_chain_rot6d": [P, I64, F32, P, I64, P, I64, P, P, P, P, P, P, P, P, P, I64, P],
     "gait_smpl_blend": [P, P, P, I64, I64, I64, P],
     "gait_smpl_lbs": [P, I64, P, P, P, I64, I64, P],
     "gait_smpl_lbs_pack_bytes": [I64],

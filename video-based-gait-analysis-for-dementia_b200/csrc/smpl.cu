@@ -19,8 +19,14 @@ constexpr int NB = GAIT_NUM_BETAS;       // 10
 // ------------------------------------------------------------------------------------------
 constexpr int kChainWarps = 4;
 
+// Optional fusions (the regression head runs them as ONE launch instead of rot6d + chain + theta):
+//   x6 != NULL : the rotations come from the 6-D representation (geometry.py:395-410), row f at x6 + f * ldx6, joint j at
+//                + 6 j, and are also written to R_out (F,24,3,3);
+//   theta != NULL : theta (F,85) = [cam | axis-angle(72) | betas] (spin.py:288, pare.py:79) with the geometry.py:68-97 route.
 __global__ void __launch_bounds__(kChainWarps * 32)
-smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ betas, int64_t ldb,
+smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ x6, int64_t ldx6, float eps6,
+                       float* __restrict__ R_out, const float* __restrict__ betas, int64_t ldb,
+                       const float* __restrict__ cam, int64_t ldcam, float* __restrict__ theta,
                        const float* __restrict__ J_template, const float* __restrict__ J_shapedirs,
                        const int32_t* __restrict__ parents, float* __restrict__ A, float* __restrict__ J_posed,
                        float* __restrict__ coef, float* __restrict__ Aop, int64_t F) {
@@ -45,8 +51,34 @@ smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ be
 
     // rotation of this joint
     float r[9];
+    if (x6) {
+        const float2* p = reinterpret_cast<const float2*>(x6 + f * ldx6 + j * 6);      // 24-byte records, 8-byte aligned
+        const float2 a0 = p[0], a1 = p[1], a2 = p[2];
+        const float in[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
+        rot6d_to_rotmat_dev(in, eps6, r);
+        if (active) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) r[k] = R[(f * NJ + j) * 9 + k];
+            for (int k = 0; k < 9; ++k) R_out[(f * NJ + j) * 9 + k] = r[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) r[k] = R[(f * NJ + j) * 9 + k];
+    }
+    if (theta) {
+        // lane k < 24 converts its rotation, lanes 24..26 copy the camera, lanes 27..31 two betas each
+        float* th = theta + f * 85;
+        if (lane < NJ) {
+            float aa[3];
+            rotmat_to_axis_angle_dev(r, 3, aa);
+            th[3 + lane * 3] = aa[0]; th[3 + lane * 3 + 1] = aa[1]; th[3 + lane * 3 + 2] = aa[2];
+        } else if (lane < NJ + 3) {
+            th[lane - NJ] = cam[f * ldcam + (lane - NJ)];
+        } else {
+            const int q = (lane - NJ - 3) * 2;
+            th[75 + q] = betas[f * ldb + q];
+            th[75 + q + 1] = betas[f * ldb + q + 1];
+        }
+    }
 
     // rest joint: J = J_template + J_shapedirs . beta
     float b[NB];
@@ -300,58 +332,81 @@ joint_regress_kernel(const float* __restrict__ verts, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// Joint assembly + projection + Kinect-25 gather: one thread per (frame, output joint).
+// Joint assembly + projection + Kinect-25 gather.  A block handles JA_FB frames: first the extra joints' partial sums
+// (one per vertex tile when the regressor row was fused into skinning: 54 strided values per coordinate) are reduced by
+// groups of 8 lanes into shared memory, then one thread per (frame, output joint) gathers / projects.
 // ------------------------------------------------------------------------------------------
+constexpr int JA_FB = 8;             // frames per block
+constexpr int JA_MAX_EXTRA = 9;      // J_regressor_extra rows
 struct ExtraJoints {
     const float* data;       // (parts, F, n_extra, 3): partial sums over vertex tiles, or one complete part
     int n_extra, parts;
     int64_t part_stride;
 };
 
-__device__ __forceinline__ void fetch_virtual_joint(int v, int64_t f, const float* __restrict__ J_posed,
+__device__ __forceinline__ void fetch_virtual_joint(int v, int64_t f, int fl, const float* __restrict__ J_posed,
                                                     const float* __restrict__ verts, int64_t V,
                                                     const int32_t* __restrict__ landmarks, int n_landmarks,
-                                                    const ExtraJoints& ex, float* o) {
+                                                    const float (*ex_s)[JA_MAX_EXTRA * 3], float* o) {
     if (v >= NJ + n_landmarks) {
-        const float* p = ex.data + (f * ex.n_extra + (v - NJ - n_landmarks)) * 3;
-        float x = 0.f, y = 0.f, z = 0.f;
-        for (int q = 0; q < ex.parts; ++q, p += ex.part_stride) { x += p[0]; y += p[1]; z += p[2]; }
-        o[0] = x; o[1] = y; o[2] = z;
+        const float* p = ex_s[fl] + (v - NJ - n_landmarks) * 3;
+        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
         return;
     }
     const float* p = (v < NJ) ? J_posed + (f * NJ + v) * 3 : verts + (f * V + landmarks[v - NJ]) * 3;
     o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
 }
 
-__global__ void joints_assemble_kernel(const float* __restrict__ J_posed, const float* __restrict__ verts, int64_t V,
-                                       const int32_t* __restrict__ landmarks, int n_landmarks,
-                                       ExtraJoints ex,
-                                       const int32_t* __restrict__ joint_map, int J, float* __restrict__ joints,
-                                       const float* __restrict__ cam, int64_t ldcam, float focal, float res,
-                                       float divisor, float* __restrict__ kp2d, const int32_t* __restrict__ gather,
-                                       int n_gather, float* __restrict__ gathered, int64_t F) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int per = J + n_gather;
-    if (i >= F * per) return;
-    const int64_t f = i / per;
-    const int k = (int)(i % per);
-    float p[3];
-    if (k < J) {
-        fetch_virtual_joint(joint_map[k], f, J_posed, verts, V, landmarks, n_landmarks, ex, p);
-        float* o = joints + (f * J + k) * 3;
-        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-        if (kp2d) {
-            const float* c = cam + f * ldcam;
-            float q[2];
-            project_point(p[0], p[1], p[2], c[1], c[2], weak_persp_tz(c[0], focal, res), focal, 0.f, 0.f, divisor, q);
-            reinterpret_cast<float2*>(kp2d)[f * J + k] = make_float2(q[0], q[1]);
+__global__ void __launch_bounds__(256)
+joints_assemble_kernel(const float* __restrict__ J_posed, const float* __restrict__ verts, int64_t V,
+                       const int32_t* __restrict__ landmarks, int n_landmarks, ExtraJoints ex,
+                       const int32_t* __restrict__ joint_map, int J, float* __restrict__ joints,
+                       const float* __restrict__ cam, int64_t ldcam, float focal, float res,
+                       float divisor, float* __restrict__ kp2d, const int32_t* __restrict__ gather,
+                       int n_gather, float* __restrict__ gathered, int64_t F) {
+    __shared__ float ex_s[JA_FB][JA_MAX_EXTRA * 3];
+    const int64_t f0 = (int64_t)blockIdx.x * JA_FB;
+    const int nf = (int)min((int64_t)JA_FB, F - f0);
+    // phase 1: sum the partial extra joints; 8 consecutive lanes share one (frame, joint, coordinate)
+    const int n_sums = nf * ex.n_extra * 3;
+    const int sub = threadIdx.x & 7;
+    for (int base = 0; base < n_sums; base += 32) {                      // 256 threads = 32 groups of 8 lanes
+        const int q = base + (threadIdx.x >> 3);
+        float a = 0.f;
+        if (q < n_sums) {
+            const int fl = q / (ex.n_extra * 3), r = q % (ex.n_extra * 3);
+            const float* p = ex.data + ((f0 + fl) * ex.n_extra) * 3 + r;
+            for (int part = sub; part < ex.parts; part += 8) a += p[part * ex.part_stride];
         }
-    } else {
-        const int g = gather[k - J];
-        if (g >= 0) fetch_virtual_joint(joint_map[g], f, J_posed, verts, V, landmarks, n_landmarks, ex, p);
-        else { p[0] = 0.f; p[1] = 0.f; p[2] = 0.f; }
-        float* o = gathered + (f * n_gather + (k - J)) * 3;
-        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (q < n_sums && sub == 0) ex_s[q / (ex.n_extra * 3)][q % (ex.n_extra * 3)] = a;
+    }
+    __syncthreads();
+    // phase 2: one thread per (frame, output slot)
+    const int per = J + n_gather;
+    for (int i = threadIdx.x; i < nf * per; i += blockDim.x) {
+        const int fl = i / per, k = i % per;
+        const int64_t f = f0 + fl;
+        float p[3];
+        if (k < J) {
+            fetch_virtual_joint(joint_map[k], f, fl, J_posed, verts, V, landmarks, n_landmarks, ex_s, p);
+            float* o = joints + (f * J + k) * 3;
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+            if (kp2d) {
+                const float* c = cam + f * ldcam;
+                float q[2];
+                project_point(p[0], p[1], p[2], c[1], c[2], weak_persp_tz(c[0], focal, res), focal, 0.f, 0.f, divisor, q);
+                reinterpret_cast<float2*>(kp2d)[f * J + k] = make_float2(q[0], q[1]);
+            }
+        } else {
+            const int g = gather[k - J];
+            if (g >= 0) fetch_virtual_joint(joint_map[g], f, fl, J_posed, verts, V, landmarks, n_landmarks, ex_s, p);
+            else { p[0] = 0.f; p[1] = 0.f; p[2] = 0.f; }
+            float* o = gathered + (f * n_gather + (k - J)) * 3;
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        }
     }
 }
 
@@ -393,8 +448,24 @@ int gait_smpl_pose_chain(const float* R, const float* betas, int64_t ldb, const 
     GAIT_REQUIRE(ldb >= NB, "smpl_pose_chain: ldb < 10");
     GAIT_REQUIRE(A == nullptr || aligned16(A), "smpl_pose_chain: A must be 16-byte aligned");
     smpl_pose_chain_kernel<<<(unsigned)ceil_div(F, kChainWarps), kChainWarps * 32, 0, as_stream(stream)>>>(
-        R, betas, ldb, J_template, J_shapedirs, parents, A, J_posed, coef, Aop, F);
+        R, nullptr, 0, 0.f, nullptr, betas, ldb, nullptr, 0, nullptr, J_template, J_shapedirs, parents, A, J_posed, coef, Aop, F);
     return check_launch("smpl_pose_chain");
+}
+
+int gait_smpl_pose_chain_rot6d(const float* x6, int64_t ldx6, float eps, const float* betas, int64_t ldb, const float* cam,
+                               int64_t ldcam, const float* J_template, const float* J_shapedirs, const int32_t* parents,
+                               float* R_out, float* A, float* J_posed, float* coef, float* Aop, float* theta, int64_t F,
+                               gait_stream_t stream) {
+    GAIT_REQUIRE(F >= 0, "smpl_pose_chain_rot6d: negative F");
+    if (F == 0) return GAIT_OK;
+    GAIT_REQUIRE(x6 && R_out && betas && J_template && J_shapedirs && parents && J_posed && (A || Aop),
+                 "smpl_pose_chain_rot6d: null pointer");
+    GAIT_REQUIRE(ldx6 >= 6 * NJ && (ldx6 & 1) == 0 && aligned8(x6) && ldb >= NB, "smpl_pose_chain_rot6d: bad stride or alignment");
+    GAIT_REQUIRE(theta == nullptr || (cam && ldcam >= 3), "smpl_pose_chain_rot6d: theta needs cam");
+    GAIT_REQUIRE(A == nullptr || aligned16(A), "smpl_pose_chain_rot6d: A must be 16-byte aligned");
+    smpl_pose_chain_kernel<<<(unsigned)ceil_div(F, kChainWarps), kChainWarps * 32, 0, as_stream(stream)>>>(
+        nullptr, x6, ldx6, eps, R_out, betas, ldb, cam, ldcam, theta, J_template, J_shapedirs, parents, A, J_posed, coef, Aop, F);
+    return check_launch("smpl_pose_chain_rot6d");
 }
 
 int gait_smpl_blend(const float* coef, const float* basis_t, float* v_posed, int64_t ldv, int64_t F, int64_t V3,
@@ -442,8 +513,8 @@ int gait_joints_assemble(const float* J_posed, const float* verts, int64_t V, co
     GAIT_REQUIRE(n_extra == 0 || (extra && extra_parts >= 1), "joints_assemble: n_extra > 0 needs extra and extra_parts >= 1");
     GAIT_REQUIRE(kp2d == nullptr || (cam && ldcam >= 3 && aligned8(kp2d)), "joints_assemble: kp2d needs cam");
     GAIT_REQUIRE(n_gather == 0 || (gather && gathered), "joints_assemble: gather needs output");
-    const int64_t n = F * (J + n_gather);
-    joints_assemble_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+    GAIT_REQUIRE(n_extra <= JA_MAX_EXTRA, "joints_assemble: at most 9 extra joints");
+    joints_assemble_kernel<<<(unsigned)ceil_div(F, JA_FB), 256, 0, as_stream(stream)>>>(
         J_posed, verts, V, landmarks, n_landmarks, ExtraJoints{extra, n_extra, extra_parts, extra_part_stride}, joint_map, J,
         joints, cam, ldcam, focal_length,
         img_res, kp2d_divisor, kp2d, gather, n_gather, gathered, F);

@@ -153,11 +153,11 @@ class GaitHead(nn.Module):
                 "gait_hmr_regressor", ptr(p["enc"]), H, ptr(rk["W1x"]), ptr(rk["W1s"]), ptr(rk["b1"]), ptr(rk["W2"]),
                 ptr(rk["b2"]), ptr(rk["Wd"]), ptr(rk["bd"]), ptr(rk["init"]), 1, self.n_iter, ptr(p["state"]), F,
                 rk["din"], rk["dh"], ptr(p["ws"]), p["hmr_bytes"], st())),
-            ("rot6d", lambda: call(
-                "gait_rot6d_to_rotmat", state, 24, _STATE_LD, ptr(p["rotmat"]), F * 24, 1e-6, st())),
+            # rot6d -> R, kinematic chain, blend coefficients, skinning operand and theta in ONE launch
             ("pose_chain", lambda: call(
-                "gait_smpl_pose_chain", ptr(p["rotmat"]), betas, _STATE_LD, ptr(sk["J_template"]),
-                ptr(sk["J_shapedirs"]), ptr(sk["parents"]), None, ptr(p["Jp"]), ptr(p["coef"]), ptr(p["aop"]), F, st())),
+                "gait_smpl_pose_chain_rot6d", state, _STATE_LD, 1e-6, betas, _STATE_LD, cam, _STATE_LD, ptr(sk["J_template"]),
+                ptr(sk["J_shapedirs"]), ptr(sk["parents"]), ptr(p["rotmat"]), None, ptr(p["Jp"]), ptr(p["coef"]), ptr(p["aop"]),
+                ptr(p["theta"]), F, st())),
             ("blend", lambda: call(
                 "gait_smpl_blend", ptr(p["coef"]), ptr(sk["basis_t"]), ptr(p["v_posed"]), sk["ldv"], F, 3 * V, st())),
             ("lbs", (lambda: call(
@@ -175,8 +175,6 @@ class GaitHead(nn.Module):
                 ptr(p["extra"]), 1, sk["vtiles"], F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
                 5000., 224., 112.,
                 ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st()))),
-            ("theta", lambda: call(
-                "gait_pack_theta", ptr(p["rotmat"]), cam, _STATE_LD, betas, _STATE_LD, ptr(p["theta"]), F, st())),
         ]
 
     def _launch(self, p):
