@@ -1,17 +1,19 @@
 // The recurrence of one torch.nn.GRU layer/direction (TemporalEncoder; gait_feat_encoder.py:51-57,88) as ONE
 // persistent kernel: all T steps, the hidden-state GEMM h_{t-1}.W_hh^T on tcgen05 in FP32-accurate split-TF32
-// form, the gate math and the TemporalEncoder residual, with a grid-wide barrier between steps.
+// form, the gate math and the TemporalEncoder residual; steps are chained by per-CTA release/acquire flags.
 //
 // Decomposition (H = 2048: 128 CTAs = 64 clusters of 2, one CTA per SM, all co-resident):
 //   * a cluster of KG = 2 CTAs owns 32 hidden units = 96 rows of W_hh (r, z and n gate rows of those units);
 //     CTA `kr` of the cluster contracts the K-slice [kr*H/2, (kr+1)*H/2) of those rows against the same slice of
 //     h_{t-1} for all (<= 64) sequences, so per step a CTA streams 96 x H/2 weights (L2-resident: W_hh is read
 //     T times) and only 64 x H/2 of the hidden state.
-//   * operands: A = [h_hi ; h_lo] (64 + 64 rows) lives in TENSOR MEMORY (written by tcgen05.st, read by TS-mode
-//     MMAs), B = W_hi then W_lo (96 rows) in shared memory: two M128 N96 K8 MMAs per k-step give h_hi.W + h_lo.W
-//     in TMEM lanes 0-63 / 64-127 (all four split products).  Split: hi = the raw FP32 word (the tensor core
-//     ignores the low 13 mantissa bits), lo = RN_tf32(x - trunc(x)), so only W_lo is ever written to shared
-//     memory - the shared-memory pipe (LDS/STS + UMMA operand reads), not the tensor pipe, bounds this kernel.
+//   * operands: A = [h_hi ; h_lo] (64 + 64 rows) lives in TENSOR MEMORY (TMA loads h and h_lo - the latter written
+//     by the finalising threads of the previous step - and the converter warps move the rows with tcgen05.st;
+//     TS-mode MMAs read them), B = W_hi then W_lo (96 rows) in shared memory: two M128 N96 K8 MMAs per k-step
+//     give h_hi.W + h_lo.W in TMEM lanes 0-63 / 64-127 (all four split products).  Split: hi = the raw FP32 word
+//     (the tensor core ignores the low 13 mantissa bits), lo = RN_tf32(x - trunc(x)), so only W_lo is ever
+//     written to shared memory by a thread (the first version was bound by the shared-memory pipe: LDS/STS +
+//     UMMA operand reads).
 //     The tensor core truncates when it adds into its FP32 accumulator, so every 64 k the partial sum is drained
 //     (tcgen05.ld) and added round-to-nearest into FP32 registers (same scheme as linear_tc.cu).
 //   * end of step: hi + lo rows are combined through shared memory, the two K-slice partials through
@@ -19,8 +21,9 @@
 //     of the cluster for 32 of the 64 sequences: gates, h_t, h_t + residual, with h_{t-1} kept in registers.
 //   * h_t goes to y (the API output) and is read back by TMA at the next step.  There is no grid-wide barrier:
 //     k-block kb of a K-slice needs exactly the 32 units one cluster produces, so every CTA publishes a step
-//     flag (st.release.gpu) and the h producer polls the KG flags of that cluster (ld.acquire.gpu) before the
-//     TMA load; the W tiles of the next step are prefetched and converted while those flags are awaited.
+//     flag (st.release.gpu, one 128-byte line per CTA) and the h producer polls the flags of the clusters it
+//     needs (relaxed loads + one acquire fence) before the TMA loads; the W tiles of the next step are prefetched
+//     while those flags are awaited.
 // Warp roles: 0 = W TMA producer, 1 and 3 = MMA issuers (even / odd accumulator chunks; 1 owns TMEM), 2 = h TMA producer (polls the flags),
 // 4-11 = promotion + gates (256 threads), 12-19 = converters (two groups of 4 warps alternating k-blocks).
 #include <cuda.h>
