@@ -93,13 +93,13 @@ int gait_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const 
                 const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
                 gait_stream_t stream);
 
-/* Prepared weights.  The tensor-core path splits every FP32 operand into a TF32 hi part (the raw word, read truncated) and a
- * lo part; for a CONSTANT weight matrix the lo part can be computed once: gait_prepare_weight writes lo (n floats, same
- * layout as W) into the caller's buffer W_lo and registers the pair, after which every gait_linear / gait_gru_layer /
- * gait_hmr_regressor / gait_smpl_blend call whose weight pointer lies inside [W, W+n) loads the lo tiles by TMA instead of
- * recomputing them (results are bit-identical).  W and W_lo must stay allocated and unchanged until gait_release_weight(W)
- * (call it before freeing or modifying W). */
-int gait_prepare_weight(const float* W, float* W_lo, int64_t n, gait_stream_t stream);
+/* Prepared weights.  The tensor-core path splits every FP32 operand into TF32 hi and lo parts; for a CONSTANT weight matrix
+ * this is done once: gait_prepare_weight writes [hi = RN_tf32(W) | lo = RN_tf32(W - hi)] (2n floats, n a multiple of 4) into the
+ * caller's buffer W_hilo and registers it, after which every gait_linear / gait_gru_layer / gait_hmr_regressor /
+ * gait_smpl_blend call whose weight pointer lies inside [W, W+n) loads both tiles by TMA instead of converting the raw weights
+ * in shared memory (same result up to FP32 rounding; the offline split is the round-to-nearest one).  W and W_hilo must stay
+ * allocated and unchanged until gait_release_weight(W) (call it before freeing or modifying W). */
+int gait_prepare_weight(const float* W, float* W_hilo, int64_t n, gait_stream_t stream);
 int gait_release_weight(const float* W);
 
 /* Debug hook: device buffer of 64*4 uint64 that receives per-k-block pipeline timestamps (stage free, data

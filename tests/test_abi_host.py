@@ -94,7 +94,7 @@ def test_new_entry_points_validate_without_gpu(lib):
     assert lib.gait_locally_connected(C.c_void_p(16), 1, 1, 1, C.c_void_p(16), 1, 1, 1, None, 0, 0, C.c_void_p(16), 1, 1, 1,
                                       C.c_void_p(16), None, 2, 3, 4, 24, None) == -1          # resid without out2
     assert lib.gait_activation(C.c_void_p(16), C.c_void_p(16), 8, 7, 0.0, None) == -1
-    assert lib.gait_prepare_weight(None, None, 0, None) == 0 and lib.gait_prepare_weight(None, None, 5, None) == -1
+    assert lib.gait_prepare_weight(None, None, 0, None) == 0 and lib.gait_prepare_weight(None, None, 8, None) == -1
     assert lib.gait_release_weight(C.c_void_p(16)) == 0
     assert lib.gait_launch_count() == n0
 

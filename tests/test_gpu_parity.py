@@ -118,9 +118,9 @@ def test_linear_vs_torch_fp32(M, N, K, lib_loaded):
     assert maxerr(Cd, (A.double() @ W.double().T + Cin.double()).float()) <= 2e-5 * max(1.0, K ** 0.5 / 8)
 
 
-def test_prepared_weight_is_bit_identical(lib_loaded):
-    """gait_prepare_weight only moves the lo-part computation out of the kernel: same bits with and without it, also for a
-    view into the registered array; releasing restores the in-kernel path."""
+def test_prepared_weight_matches_unprepared(lib_loaded):
+    """gait_prepare_weight moves the weight split out of the kernel (offline round-to-nearest split): same result up to FP32
+    rounding, also for a view into the registered array; releasing restores the in-kernel path bit for bit."""
     L = lib_loaded
     g = torch.Generator().manual_seed(5)
     M, N, K = 300, 320, 256
@@ -135,7 +135,8 @@ def test_prepared_weight_is_bit_identical(lib_loaded):
     L.release_weight(Wbig)
     run(out2)
     torch.cuda.synchronize()
-    assert torch.equal(out0, out1) and torch.equal(out0, out2)
+    assert torch.equal(out0, out2) and maxerr(out0, out1) <= 4e-6
+    assert maxerr(out1, (A.double() @ W.double().T).float()) <= 2e-5
     assert maxerr(out0, (A.double() @ W.double().T).float()) <= 2e-5
 
 
@@ -507,6 +508,35 @@ def test_head_joints_only_c5(lib_loaded):
         ref = GaitHeadOracle(data, mean, rs, gs)(feats)
         assert maxerr(b["kinect25"], ref["kinect25"]) <= TOL_V
         assert maxerr(b["kp_2d"], ref["kp_2d"]) <= TOL_2D
+
+
+def _oracle_fp64(oracle, feats):
+    """The same oracle evaluated in FP64 (its few in-line constants follow the default dtype)."""
+    import copy
+    o64 = copy.deepcopy(oracle).double()
+    torch.set_default_dtype(torch.float64)
+    try:
+        return o64(feats.double())
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("S", [100, 200])
+def test_head_c3_shard_sizes(S, lib_loaded):
+    """BASELINE config 3 shards (128 / 256 / 512 sequences per GPU): 100 sequences run the persistent recurrence as two
+    64-sequence launches, 200 take the per-step path.  Over thousands of frames the FP32 oracle's own rounding reaches the
+    rotation tolerance on the worst-conditioned frame (6-D vectors with a short first column; measured 9.7e-6 at S = 100
+    between the oracle in FP32 and in FP64), so the bound is anchored on the exact value: the CUDA path is within the stated
+    tolerance of the FP64 evaluation, and within tolerance + the oracle's own FP32 deviation of the FP32 oracle."""
+    head, oracle, _ = _heads()
+    feats = synthetic.make_features(S, 16, seed=9)
+    out = head(feats.cuda())
+    ref32, ref64 = oracle(feats), _oracle_fp64(oracle, feats)
+    for key, tol in (("rotmat", TOL_R), ("verts", TOL_V), ("kp_3d", TOL_V), ("kinect25", TOL_V), ("kp_2d", TOL_2D), ("theta", TOL_AA)):
+        got = out[key].cpu().double()
+        own = (ref32[key].double() - ref64[key]).abs().max().item()
+        assert (got - ref64[key]).abs().max().item() <= tol, key
+        assert (got - ref32[key].double()).abs().max().item() <= tol + own, key
 
 
 def test_head_long_clip_c4(lib_loaded):

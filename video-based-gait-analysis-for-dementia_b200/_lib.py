@@ -137,7 +137,9 @@ def prepare_weight(w: torch.Tensor) -> torch.Tensor:
         return w
     if hit is not None:
         _drop_prepared(key)
-    lo = torch.empty(w.shape, device=w.device, dtype=torch.float32)
+    if w.numel() % 4:
+        return w                                  # not TMA-addressable anyway
+    lo = torch.empty((2,) + tuple(w.shape), device=w.device, dtype=torch.float32)    # [hi | lo]
     call("gait_prepare_weight", key, ptr(lo), w.numel(), stream_ptr())
     _prepared[key] = (weakref.ref(w, lambda _r, k=key: _drop_prepared(k)), lo, w._version)
     return w

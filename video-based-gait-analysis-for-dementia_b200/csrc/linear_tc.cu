@@ -41,7 +41,8 @@ constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int MAX_STAGES = 4;
 constexpr int BOX_ROWS = 32;               // rows per TMA box: the rows of a box are fetched serially, boxes in parallel
-constexpr int DRAIN_KB = 2;               // k-blocks accumulated in TMEM between promotions to FP32 registers
+constexpr int DRAIN_KB_LONG_K = 1;        // k-blocks accumulated in TMEM between promotions to FP32 registers when K >= 512 ...
+constexpr int DRAIN_KB_SHORT_K = 2;       // ... and for short contractions (few truncating accumulations anyway; the blend GEMM)
 constexpr int THREADS = 640;              // 20 warps, see the kernel comment
 
 constexpr int NDRAIN = 256;
@@ -167,14 +168,14 @@ enum : int { B_FULL = 0, B_CONV = MAX_STAGES, B_EMPTY = 2 * MAX_STAGES, B_ACC_FU
 //   4-11   promotion + epilogue: warp -> TMEM lane quadrant (warp & 3) x column half ((warp - 4) >> 2)
 //   12-19  converters: two groups of four warps (all quadrants each), even / odd k-blocks
 //
-// QLO = true: the lo parts of the BN-row operand (constant weights) were split off once (gait_prepare_weight); they are
-// loaded by TMA next to the raw tile and the converters only handle the 128-row operand.
+// QLO = true: the BN-row operand (constant weights) was split once (gait_prepare_weight: round-to-nearest hi and lo arrays);
+// both tiles are loaded by TMA and the converters only handle the 128-row operand.
 template <int BN, bool QLO>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ,
                    const __grid_constant__ CUtensorMap tmQlo, const float* __restrict__ bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
                    int P_rows, int Q_rows, int K, int transposed, int kb_per_split, int64_t split_stride,
-                   int tiles_p, int splits, int n_items, int mode, unsigned long long* trace) {
+                   int tiles_p, int splits, int n_items, int mode, int drain, unsigned long long* trace) {
     using cfg = Cfg<BN>;
     constexpr int STAGES = cfg::STAGES;
     constexpr int HN = BN / 2;                                   // accumulator columns per promotion warp
@@ -188,7 +189,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb_total = (K + BK - 1) / BK;
-    const int drain_kb = (mode == 2) ? (1 << 30) : DRAIN_KB;          // mode 2 (debug): never promote
+    const int drain_kb = (mode == 2) ? (1 << 30) : drain;          // mode 2 (debug): never promote
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -266,17 +267,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 const bool last_of_chunk = (kb % drain_kb) == drain_kb - 1 || kb == nkb - 1;
                 if (elect_one()) {
                     if (trace && blockIdx.x == 0 && it + kb < 64) trace[(it + kb) * 4 + 2] = clock64();
+                    // The tensor core truncates the FP32 accumulator after every MMA, an error proportional to the accumulator's
+                    // magnitude: the small cross terms go first (into a still-small accumulator at the start of a chunk), the
+                    // hi*hi products last.
+                    if (mode != 1) {
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 floats = 32 bytes along K inside the swizzle span
+                            umma_tf32_ts(acc, p_lo + 8 * k, q_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                            umma_tf32_ts(acc, p_hi + 8 * k, q_lo + adv, idesc, 1u);
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 floats = 32 bytes along K inside the swizzle span
-                        const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
-                        if (mode == 1) {                                    // debug: plain TF32
-                            umma_tf32_ts(acc, p_hi + 8 * k, q_hi + adv, idesc, first);
-                        } else {
-                            umma_tf32_ts(acc, p_lo + 8 * k, q_hi + adv, idesc, first);
-                            umma_tf32_ts(acc, p_hi + 8 * k, q_lo + adv, idesc, 1u);
-                            umma_tf32_ts(acc, p_hi + 8 * k, q_hi + adv, idesc, 1u);
-                        }
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                        umma_tf32_ts(acc, p_hi + 8 * k, q_hi + adv, idesc, (mode == 1 && chunk_start && k == 0) ? 0u : 1u);
                     }
                     umma_commit(BAR(B_EMPTY + s));                          // frees the stage when the MMAs retire
                     if (last_of_chunk) umma_commit(BAR(B_ACC_FULL + buf));
@@ -306,10 +311,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                         r[4 * c] = __float_as_uint(x.x); r[4 * c + 1] = __float_as_uint(x.y);
                         r[4 * c + 2] = __float_as_uint(x.z); r[4 * c + 3] = __float_as_uint(x.w);
                     }
+                    // this operand goes through registers anyway, so it gets the round-to-nearest split
+                    // (hi = RN_tf32(x), lo = RN_tf32(x - hi): |x - hi - lo| <= 2^-23 |x|, |lo| <= 2^-11 |x|)
                     const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cfg::TMEM_P0 + s * cfg::P_COLS);
-                    tmem_st32(ta, r);
+                    uint32_t h[BK];
 #pragma unroll
-                    for (int j = 0; j < BK; ++j) r[j] = __float_as_uint(tf32_lo(__uint_as_float(r[j])));
+                    for (int j = 0; j < BK; ++j) h[j] = __float_as_uint(tf32_hi(__uint_as_float(r[j])));
+                    tmem_st32(ta, h);
+#pragma unroll
+                    for (int j = 0; j < BK; ++j) r[j] = __float_as_uint(tf32_hi(__uint_as_float(r[j]) - __uint_as_float(h[j])));
                     tmem_st32(ta + BK, r);
                 }
                 // Q: lo tile only (the raw tile is the hi operand); nothing to do for prepared weights
@@ -334,8 +344,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         } else if (warp >= 4) {
             // ------------------------------------------------------------ promotion + epilogue
             // The tensor core adds into its FP32 accumulator with truncation, so error grows linearly
-            // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every DRAIN_KB
-            // k-blocks the TMEM partial sum is therefore added (round-to-nearest) into FP32 registers.
+            // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every `drain_kb`
+            // k-blocks the TMEM partial sum is therefore added (round-to-nearest) into FP32 registers
+            // (measured mean error against FP64 at K = 2048: 1.9e-7 relative with 1 k-block, 3.7e-7 with 2;
+            // cuBLAS FP32 7.1e-7).
             const int quad = warp & 3;                              // this warp owns TMEM lanes 32*quad .. +31
             const int half = (warp - 4) >> 2;                       // ... and accumulator columns half*HN .. +HN-1
             float accr[HN];
@@ -479,7 +491,7 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
     }
     gemm_tf32x3_kernel<BN, QLO><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
                                                                      transposed, kb_per_split, split_stride, tiles_p, splits,
-                                                                     n_items, mode, g_trace);
+                                                                     n_items, mode, K >= 512 ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K, g_trace);
     return check_launch("linear(tf32x3 tcgen05)");
 }
 
@@ -495,22 +507,30 @@ bool linear_tc_eligible(const float* A, int64_t lda, const float* W, int64_t ldw
 
 // ---- prepared weights: lo parts split off once per model (gait_prepare_weight) --------------------------------------------
 namespace {
-struct PreparedWeight { const float* base; const float* lo; int64_t n; };
+struct PreparedWeight { const float* base; const float* hilo; int64_t n; };     // hilo: [RN hi (n) | lo (n)]
 std::mutex g_prep_mutex;
 std::vector<PreparedWeight> g_prepared;
 }  // namespace
 
-// lo pointer matching W (which may point inside a registered array), or nullptr
-static const float* find_prepared_lo(const float* W, int64_t n_needed) {
+// prepared hi / lo pointers matching W (which may point inside a registered array); false when W is not prepared
+static bool find_prepared(const float* W, int64_t n_needed, const float** hi, const float** lo) {
     std::lock_guard<std::mutex> lock(g_prep_mutex);
     for (const auto& e : g_prepared)
-        if (W >= e.base && W + n_needed <= e.base + e.n) return e.lo + (W - e.base);
-    return nullptr;
+        if (W >= e.base && W + n_needed <= e.base + e.n) {
+            *hi = e.hilo + (W - e.base);
+            *lo = e.hilo + e.n + (W - e.base);
+            return true;
+        }
+    return false;
 }
 
-__global__ void split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t n) {
+// round-to-nearest split, done once for constant weights: hi = RN_tf32(x), lo = RN_tf32(x - hi)
+__global__ void split_hilo_kernel(const float* __restrict__ x, float* __restrict__ hilo, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) lo[i] = tc::tf32_lo(x[i]);
+    if (i >= n) return;
+    const float v = x[i], h = tc::tf32_hi(v);
+    hilo[i] = h;
+    hilo[n + i] = tc::tf32_hi(v - h);
 }
 
 // splits > 1: C must hold `splits` partial results `split_stride` floats apart; bias/Cin go into split 0.
@@ -531,14 +551,15 @@ int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, c
     }
     const int bn = (ceil_div(M, BM) * ceil_div(N, 128) < 120 && N > 64) ? 64 : 128;
     GAIT_TRY(make_map(&tmP, A, M, K, lda, BM));
-    GAIT_TRY(make_map(&tmQ, W, N, K, ldw, bn));
-    const float* Wlo = find_prepared_lo(W, (N - 1) * ldw + K);
-    if (Wlo && aligned16(Wlo)) {
+    const float *Whi = nullptr, *Wlo = nullptr;
+    if (find_prepared(W, (N - 1) * ldw + K, &Whi, &Wlo) && aligned16(Whi) && aligned16(Wlo)) {
+        GAIT_TRY(make_map(&tmQ, Whi, N, K, ldw, bn));          // the prepared hi array replaces the raw weights
         GAIT_TRY(make_map(&tmQlo, Wlo, N, K, ldw, bn));
         if (bn == 64)
             return launch<64, true>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
         return launch<128, true>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
     }
+    GAIT_TRY(make_map(&tmQ, W, N, K, ldw, bn));
     if (bn == 64)
         return launch<64, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
     return launch<128, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
@@ -548,14 +569,16 @@ int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, c
 
 extern "C" {
 
-int gait_prepare_weight(const float* W, float* W_lo, int64_t n, gait_stream_t stream) {
-    GAIT_REQUIRE(n >= 0 && (n == 0 || (W && W_lo)), "prepare_weight: null pointer or negative size");
+int gait_prepare_weight(const float* W, float* W_hilo, int64_t n, gait_stream_t stream) {
+    float* W_lo = W_hilo;
+    GAIT_REQUIRE(n >= 0 && (n == 0 || (W && W_hilo)), "prepare_weight: null pointer or negative size");
+    GAIT_REQUIRE((n & 3) == 0 && gait::aligned16(W_hilo), "prepare_weight: n must be a multiple of 4 and the split buffer 16-byte aligned");
     if (n == 0) return GAIT_OK;
-    gait::split_lo_kernel<<<(unsigned)gait::ceil_div(n, 256), 256, 0, gait::as_stream(stream)>>>(W, W_lo, n);
+    gait::split_hilo_kernel<<<(unsigned)gait::ceil_div(n, 256), 256, 0, gait::as_stream(stream)>>>(W, W_hilo, n);
     GAIT_TRY(gait::check_launch("prepare_weight"));
     std::lock_guard<std::mutex> lock(gait::g_prep_mutex);
     for (auto& e : gait::g_prepared)
-        if (e.base == W) { e.lo = W_lo; e.n = n; return GAIT_OK; }
+        if (e.base == W) { e.hilo = W_lo; e.n = n; return GAIT_OK; }
     gait::g_prepared.push_back({W, W_lo, n});
     return GAIT_OK;
 }
