@@ -9,6 +9,8 @@ from gaitb200 import _lib as L
 L.require_device()
 for (M, N, K) in [(1024, 6144, 2048), (64, 6144, 2048), (1024, 1024, 1024)]:
     A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda"); C = torch.empty(M, N, device="cuda")
+    if "--prepared" in sys.argv:
+        L.prepare_weight(W)
     tr = torch.zeros(64 * 4, dtype=torch.int64, device="cuda")
     for rep in range(3):
         tr.zero_()
@@ -20,7 +22,7 @@ for (M, N, K) in [(1024, 6144, 2048), (64, 6144, 2048), (1024, 1024, 1024)]:
     t0 = int(t[0, 0])
     print(f"--- M={M} N={N} K={K}: kb: stage_free  landed(+L)  converted(+C)  mma_issued | period")
     prev = None
-    for kb in range(min(K // 32, 24)):
+    for kb in range(min(K // 32, 40)):
         a, b, c, d = [int(x) - t0 for x in t[kb]]
         per = "" if prev is None else a - prev
         print(f"{kb:3d} {a:8d} {b - a:8d} {c - b:8d} {d - c:8d}   {per}")

@@ -46,6 +46,8 @@ constexpr int DRAIN_KB_SHORT_K = 2;       // ... and for short contractions (few
 constexpr int THREADS = 640;              // 20 warps, see the kernel comment
 
 constexpr int NDRAIN = 256;
+// register budget after the setup (setmaxnreg): 128 x 48 + 256 x 120 + 256 x 96 (converters, unchanged) = 640 x 96
+constexpr int REGS_ISSUE = 48, REGS_PROMOTE = 120;
 
 template <int BN>
 struct Cfg {
@@ -107,6 +109,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 accumulator columns in one instruction (no wait: the caller batches loads, then tcgen05.wait::ld once)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
@@ -212,20 +226,29 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    int it = 0;        // k-blocks processed so far by this CTA (position in the stage ring)
-    int ch = 0;        // accumulator chunks processed so far (position in the TMEM ring)
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        // item order: k-split fastest, then the 128-row tiles, then the BN-row (weight) tiles - CTAs that run concurrently
-        // share weight tiles, so a large weight matrix is streamed from HBM once instead of once per 128-row tile
-        const int z = item % splits;
-        const int pt = (item / splits) % tiles_p;
-        const int qt = item / (splits * tiles_p);
-        const int p0 = pt * BM, q0 = qt * BN;
-        const int kb0 = z * kb_per_split;
-        const int nkb = min(kb_per_split, nkb_total - kb0);
-        const int nchunks = (nkb + drain_kb - 1) / drain_kb;
-
+    // Every role runs its own loop over the CTA's work items (it = k-blocks processed so far = position in the stage ring,
+    // ch = accumulator chunks so far = position in the TMEM ring), so that the register budget can be re-divided per
+    // warpgroup: the promotion warps hold a 128 x BN/2 FP32 tile plus 32 freshly loaded columns.
+#define ITEM_LOOP_BEGIN                                                                                                   \
+    for (int item = blockIdx.x, it = 0, ch = 0; item < n_items; item += gridDim.x) {                                     \
+        /* item order: k-split fastest, then the 128-row tiles, then the BN-row (weight) tiles - CTAs that run            \
+           concurrently share weight tiles, so a large weight matrix is streamed from HBM once, not once per row tile */ \
+        const int z = item % splits;                                                                                      \
+        const int pt = (item / splits) % tiles_p;                                                                         \
+        const int qt = item / (splits * tiles_p);                                                                         \
+        const int p0 = pt * BM, q0 = qt * BN;                                                                             \
+        const int kb0 = z * kb_per_split;                                                                                 \
+        const int nkb = min(kb_per_split, nkb_total - kb0);                                                               \
+        const int nchunks = (nkb + drain_kb - 1) / drain_kb;                                                              \
+        (void)pt; (void)p0; (void)q0; (void)kb0; (void)nchunks; (void)ch;
+#define ITEM_LOOP_END                                                                                                     \
+        it += nkb;                                                                                                        \
+        ch += nchunks;                                                                                                    \
+    }
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ISSUE));
         if (warp == 0 || warp == 2) {
+        ITEM_LOOP_BEGIN
             // ------------------------------------------------------------ TMA producers
             // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
             // instruction occupies its warp for ~450 cycles (+ ~50 per extra active lane), the rows of one box are
@@ -247,7 +270,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 }
                 __syncwarp();
             }
-        } else if (warp == 1 || warp == 3) {
+        ITEM_LOOP_END
+        } else {
+        ITEM_LOOP_BEGIN
             // ------------------------------------------------------------ MMA issuers (warp-uniform loop, one lane issues)
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const int par = warp == 1 ? 0 : 1;
@@ -289,7 +314,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 }
                 __syncwarp();
             }
-        } else if (warp >= 12) {
+        ITEM_LOOP_END
+        }
+    } else if (warp >= 12) {
+        ITEM_LOOP_BEGIN
             // ------------------------------------------------------------ converters: FP32 -> (hi = raw word, lo)
             const int grp = (warp - 12) >> 2;
             const int quad = warp & 3;                               // TMEM lane quadrant this warp may write
@@ -341,7 +369,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
             }
-        } else if (warp >= 4) {
+        ITEM_LOOP_END
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROMOTE));
+        ITEM_LOOP_BEGIN
             // ------------------------------------------------------------ promotion + epilogue
             // The tensor core adds into its FP32 accumulator with truncation, so error grows linearly
             // with the number of MMAs per accumulator (measured: 7e-9 * K relative).  Every `drain_kb`
@@ -357,16 +388,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 const int cg = ch + chunk, buf = cg % cfg::NBUF, use = cg / cfg::NBUF;
                 mbar_wait(BAR(B_ACC_FULL + buf), use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // 32 columns per load instruction and one wait per load: with a promotion every k-block the time of this
+                // loop bounds the accumulator ring.  The buffer is handed back as soon as its last values are in registers.
 #pragma unroll
-                for (int c = 0; c < HN / 16; ++c) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * HN + c * 16), r);
+                for (int c = 0; c < HN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32_nowait(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * HN + c * 32), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (c == HN / 32 - 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + buf));
+                    }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) accr[c * 16 + j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) accr[c * 32 + j] += __uint_as_float(r[j]);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(B_ACC_EMPTY + buf));
             }
             const int prow = p0 + quad * 32 + lane;
             const bool first_split = z == 0;
@@ -436,10 +472,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     __syncwarp();
                 }
             }
-        }
-        it += nkb;
-        ch += nchunks;
+        ITEM_LOOP_END
     }
+#undef ITEM_LOOP_BEGIN
+#undef ITEM_LOOP_END
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
@@ -484,14 +520,16 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
     // persistent CTAs, one per SM; balance the number of items per CTA
     const int per_cta = (int)ceil_div(n_items, n_sms);
     dim3 grid((unsigned)ceil_div(n_items, per_cta));
-    static int mode = -1;
+    static int mode = -1, drain_override = 0;
     if (mode < 0) {
         const char* e = getenv("GAITB200_TC_MODE");
         mode = e ? atoi(e) : 0;
+        const char* d = getenv("GAITB200_TC_DRAIN");          // experiment knob: k-blocks per promotion
+        drain_override = d ? atoi(d) : 0;
     }
     gemm_tf32x3_kernel<BN, QLO><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
                                                                      transposed, kb_per_split, split_stride, tiles_p, splits,
-                                                                     n_items, mode, K >= 512 ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K, g_trace);
+                                                                     n_items, mode, drain_override > 0 ? drain_override : (K >= 512 ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K), g_trace);
     return check_launch("linear(tf32x3 tcgen05)");
 }
 
