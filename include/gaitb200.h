@@ -138,6 +138,14 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
                        int64_t Din, int64_t Dh, void* workspace, size_t workspace_bytes,
                        gait_stream_t stream);
 
+/* The same loop with the layers folded (opt-in).  spin.py:244-265 has no non-linearity between fc1, fc2 and the decoders and
+ * dropout is the identity in eval(), so for the shared mean-parameter init the n_iter iterations are ONE affine map of x:
+ * state = x . Wf^T + bf, Wf (157,Din), bf (157), folded by the caller in FP64 (gaitb200.regressor.Regressor.fold).
+ * state_out (F,160), padding columns zeroed.  Same results as gait_hmr_regressor up to FP32 rounding. */
+size_t gait_hmr_folded_workspace_bytes(int64_t F);
+int gait_hmr_regressor_folded(const float* x, int64_t ldx, const float* Wf, const float* bf, float* state_out,
+                              int64_t F, int64_t Din, void* workspace, size_t workspace_bytes, gait_stream_t stream);
+
 /* ---- SMPL: smplx==0.1.26 lbs.py via lib/models/smpl.py:108-130 ---------------------------- */
 /* Shape-dependent rest joints + 24-joint kinematic chain (smplx lbs.batch_rigid_transform), one
  * warp per frame, parent transforms exchanged by warp shuffle level by level.

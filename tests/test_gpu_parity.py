@@ -362,6 +362,54 @@ def test_regressor_vs_reference_golden(golden, smpl_data, lib_loaded):
     assert maxerr(o["kp_3d"], g["reg_h36m_kp_3d"]) <= TOL_V and maxerr(o["kp_2d"], g["reg_h36m_kp_2d"]) <= TOL_2D
 
 
+def test_regressor_folded_matches_loop(golden, smpl_data, lib_loaded):
+    """Opt-in folded regressor (one affine map instead of n_iter x (fc1, fc2, decoders)): same state as the loop and as the
+    reference golden, for 1..4 iterations; re-folded when a weight changes; padding columns zero."""
+    from gaitb200.regressor import Regressor
+    from oracle import regressor as OR
+    g = golden("regressor")
+    mean = synthetic.make_mean_params()
+    state = synthetic.make_regressor_state(seed=0, decoder_gain=0.3)
+    reg = Regressor(mean, smpl_data)
+    reg.load_state_dict(state, strict=False)
+    reg = reg.cuda().eval()
+    o = OR.Regressor(smpl_data, mean).eval()
+    o.load_state_dict(state, strict=False)
+    x = synthetic.make_features(9, 16, seed=3).reshape(144, -1)
+    for n in (1, 2, 3, 4):
+        with torch.no_grad():
+            ref = torch.cat(o.iterate(x, n_iter=n), 1)
+        st_f, st_l = reg.iterate_folded(x.cuda(), n_iter=n), reg.iterate(x.cuda(), n_iter=n)
+        assert st_f.shape == (144, 160) and float(st_f[:, 157:].abs().max()) == 0.0
+        assert maxerr(st_f[:, :157], ref) <= 2e-6 and maxerr(st_f[:, :157], st_l[:, :157]) <= 2e-6
+    # the reference's own golden: rot6d of the folded state reproduces its rotation matrices
+    from gaitb200 import geometry as GG
+    st = reg.iterate_folded(dev(g["x"]))
+    assert maxerr(GG.rot6d_to_rotmat(st[:, :144]).view(-1, 24, 3, 3), g["reg_rotmat"]) <= TOL_R
+    # a weight update invalidates the fold
+    with torch.no_grad():
+        reg.fc2.bias.add_(0.25)
+        o.fc2.bias.add_(0.25)
+        ref = torch.cat(o.iterate(x, n_iter=3), 1)
+    assert maxerr(reg.iterate_folded(x.cuda())[:, :157], ref) <= 2e-6
+    # F = 1 (SIMT path) and empty input
+    assert maxerr(reg.iterate_folded(x[:1].cuda())[:, :157], ref[:1]) <= 2e-6
+    assert reg.iterate_folded(x[:0].cuda()).shape == (0, 160)
+
+
+def test_head_folded_regressor_vs_oracle(lib_loaded):
+    """GaitHead(fold_regressor=True) on C2-sized input: every output within the stated tolerances of the oracle."""
+    from gaitb200.head import GaitHead
+    from oracle.head import GaitHeadOracle
+    data = synthetic.make_smpl_data(seed=0, variant="sparse")
+    mean = synthetic.make_mean_params()
+    rs = synthetic.make_regressor_state(seed=0, decoder_gain=0.3)
+    gs = synthetic.make_gru_state(seed=0)
+    head = GaitHead(data, mean, rs, gs, fold_regressor=True).cuda()
+    feats = synthetic.make_features(8, 16, seed=21)
+    _check_head(head(feats.cuda()), GaitHeadOracle(data, mean, rs, gs)(feats))
+
+
 def test_regressor_known_answers_and_inits(smpl_data, lib_loaded):
     from gaitb200.regressor import Regressor
     from oracle import regressor as OR

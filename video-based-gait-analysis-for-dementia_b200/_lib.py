@@ -43,6 +43,8 @@ _SIGS = {
     "gait_relu": [P, P, I64, P],
     "gait_hmr_workspace_bytes": [I64, I64],
     "gait_hmr_regressor": [P, I64, P, P, P, P, P, P, P, P, I64, I32, P, I64, I64, I64, P, SZ, P],
+    "gait_hmr_folded_workspace_bytes": [I64],
+    "gait_hmr_regressor_folded": [P, I64, P, P, P, I64, I64, P, SZ, P],
     "gait_smpl_pose_chain": [P, P, I64, P, P, P, P, P, P, P, I64, P],
     "gait_smpl_pose_chain_rot6d": [P, I64, F32, P, I64, P, I64, P, P, P, P, P, P, P, P, P, I64, P],
     "gait_smpl_blend": [P, P, P, I64, I64, I64, P],
@@ -69,6 +71,7 @@ _RESTYPES = {
     "gait_launch_count": I64,
     "gait_gru_workspace_bytes": SZ,
     "gait_hmr_workspace_bytes": SZ,
+    "gait_hmr_folded_workspace_bytes": SZ,
     "gait_smpl_lbs_pack_bytes": SZ,
     "gait_smpl_lbs_aop_bytes": SZ,
 }

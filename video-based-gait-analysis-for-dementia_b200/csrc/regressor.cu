@@ -40,6 +40,26 @@ __global__ void decoder_reduce_kernel(const float* __restrict__ part, int parts,
     state[i] += acc;
 }
 
+// state[f, c] = sum over split-K partials (partial 0 holds the bias); padding columns are zeroed
+__global__ void folded_reduce_kernel(const float* __restrict__ part, int parts, int64_t part_stride,
+                                     float* __restrict__ state, int64_t F) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= F * kStateLd) return;
+    const int c = (int)(i % kStateLd);
+    float acc = 0.f;
+    if (c < kState)
+        for (int p = 0; p < parts; ++p) acc += part[p * part_stride + i];
+    state[i] = acc;
+}
+
+static int folded_splits(const float* x, int64_t ldx, const float* Wf, int64_t F, int64_t Din) {
+    if (linear_path() == 1 || !linear_tc_eligible(x, ldx, Wf, Din, F, kState, Din)) return 1;
+    const int64_t nkb = ceil_div(Din, 32);
+    int splits = (int)std::min<int64_t>(kDecSplits, nkb);
+    while (splits > 1 && ceil_div(nkb, ceil_div(nkb, splits)) != splits) --splits;
+    return splits;
+}
+
 }  // namespace gait
 
 using namespace gait;
@@ -49,6 +69,34 @@ extern "C" {
 size_t gait_hmr_workspace_bytes(int64_t F, int64_t Dh) {
     if (F <= 0 || Dh <= 0) return 0;
     return (size_t)(3 * F * Dh + kDecSplits * F * kStateLd) * sizeof(float);
+}
+
+size_t gait_hmr_folded_workspace_bytes(int64_t F) {
+    if (F <= 0) return 0;
+    return (size_t)(kDecSplits * F * kStateLd) * sizeof(float);
+}
+
+int gait_hmr_regressor_folded(const float* x, int64_t ldx, const float* Wf, const float* bf, float* state_out,
+                              int64_t F, int64_t Din, void* workspace, size_t workspace_bytes, gait_stream_t stream) {
+    GAIT_REQUIRE(F >= 0 && Din > 0, "hmr_regressor_folded: bad sizes");
+    if (F == 0) return GAIT_OK;
+    GAIT_REQUIRE(x && Wf && bf && state_out && workspace, "hmr_regressor_folded: null pointer");
+    GAIT_REQUIRE(ldx >= Din, "hmr_regressor_folded: ldx < Din");
+    if (workspace_bytes < gait_hmr_folded_workspace_bytes(F)) {
+        set_error("hmr_regressor_folded: workspace %zu < %zu bytes", workspace_bytes, gait_hmr_folded_workspace_bytes(F));
+        return GAIT_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    float* part = static_cast<float*>(workspace);
+    // F x 157 x Din: few output tiles, so K is cut across CTAs when the tensor-core path takes it
+    const int splits = folded_splits(x, ldx, Wf, F, Din);
+    if (splits > 1) {
+        GAIT_TRY(linear_tc_launch(x, ldx, Wf, Din, bf, nullptr, 0, part, kStateLd, F, kState, Din, splits, F * kStateLd, st));
+    } else {
+        GAIT_TRY(linear_launch(x, ldx, Wf, Din, bf, nullptr, 0, part, kStateLd, F, kState, Din, st));
+    }
+    folded_reduce_kernel<<<(unsigned)ceil_div(F * kStateLd, 256), 256, 0, st>>>(part, splits, F * kStateLd, state_out, F);
+    return check_launch("hmr folded_reduce");
 }
 
 int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const float* W1s, const float* b1,

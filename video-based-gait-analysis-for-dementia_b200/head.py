@@ -45,8 +45,11 @@ class HostOutputs(dict):
 
 class GaitHead(nn.Module):
     def __init__(self, smpl_data, mean_params, regressor_state=None, gru_state=None, write_mesh=True,
-                 n_iter=3, **encoder_kw):
+                 n_iter=3, fold_regressor=False, **encoder_kw):
+        """fold_regressor: run the regressor loop as its folded affine map (Regressor.fold; opt-in, same outputs up to FP32
+        rounding, the iteration's GEMMs are gone - not the default and not what bench.py's headline measures)."""
         super().__init__()
+        self.fold_regressor = bool(fold_regressor)
         self.encoder = TemporalEncoder(**encoder_kw)
         self.regressor = Regressor(mean_params, smpl_data)
         if gru_state is not None:
@@ -144,12 +147,15 @@ class GaitHead(nn.Module):
         state = p["state"].data_ptr()
         betas, cam = state + 4 * 144, state + 4 * 154
         L.prepare_weight(gru.weight_ih_l0)
+        fk = reg.fold(self.n_iter) if self.fold_regressor else None
         return [
             ("gru", lambda: call(
                 "gait_gru_layer", ptr(p["x"]), H, ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), ptr(gru.bias_ih_l0),
                 ptr(gru.bias_hh_l0), None, ptr(p["y_raw"]), H, ptr(p["x"]), H, ptr(p["enc"]), H, None, S, T, H, H, 0,
                 ptr(p["ws"]), p["gru_bytes"], st())),
-            ("regressor", lambda: call(
+            ("regressor", (lambda: call(
+                "gait_hmr_regressor_folded", ptr(p["enc"]), H, ptr(fk["Wf"]), ptr(fk["bf"]), ptr(p["state"]), F, rk["din"],
+                ptr(p["ws"]), p["hmr_bytes"], st())) if self.fold_regressor else lambda: call(
                 "gait_hmr_regressor", ptr(p["enc"]), H, ptr(rk["W1x"]), ptr(rk["W1s"]), ptr(rk["b1"]), ptr(rk["W2"]),
                 ptr(rk["b2"]), ptr(rk["Wd"]), ptr(rk["bd"]), ptr(rk["init"]), 1, self.n_iter, ptr(p["state"]), F,
                 rk["din"], rk["dh"], ptr(p["ws"]), p["hmr_bytes"], st())),

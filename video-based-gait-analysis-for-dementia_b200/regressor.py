@@ -54,6 +54,7 @@ class Regressor(nn.Module):
         self.register_buffer('init_cam', torch.from_numpy(np.asarray(mean_params['cam'], dtype=np.float32)).unsqueeze(0))
         self._packed = None
         self._packed_key = None
+        self._folded = {}
 
     # ------------------------------------------------------------ packed weights
     def _prepare(self):
@@ -89,7 +90,52 @@ class Regressor(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self._folded = {}
         return super()._apply(fn, *a, **k)
+
+    def fold(self, n_iter=3):
+        """Opt-in weight folding.  spin.py:244-265 puts no non-linearity between fc1, fc2 and the decoders, and dropout is the
+        identity in eval(), so with the shared mean-parameter init the loop is one affine map of x:
+            u = A x + c,  s_{k+1} = (I + B) s_k + u   =>   s_n = G A x + (G c + (I + B)^n s_0),  G = sum_{k<n} (I + B)^k
+        with D = Wd W2, A = D W1x, B = D W1s, c = D b1 + Wd b2 + bd.  The products are formed once in FP64 and rounded to FP32;
+        returns {"Wf": (157,Din), "bf": (157,)} (re-folded when a weight changes)."""
+        pk = self._prepare()
+        key = (self._packed_key, int(n_iter))
+        hit = self._folded.get("key")
+        if hit == key:
+            return self._folded
+        with torch.no_grad():
+            d = lambda t: t.double()
+            W1x, W1s, W2, Wd = d(pk["W1x"]), d(pk["W1s"][:, :_STATE]), d(pk["W2"]), d(pk["Wd"])
+            D = Wd @ W2
+            A, B = D @ W1x, D @ W1s
+            c = D @ d(pk["b1"]) + Wd @ d(pk["b2"]) + d(pk["bd"])
+            T = torch.eye(_STATE, dtype=torch.float64, device=A.device) + B
+            G = torch.zeros_like(T)
+            P = torch.eye(_STATE, dtype=torch.float64, device=A.device)
+            for _ in range(int(n_iter)):
+                G += P
+                P = T @ P
+            s0 = d(pk["init"][0, :_STATE])
+            self._folded = {"key": key, "Wf": (G @ A).float().contiguous(), "bf": (G @ c + P @ s0).float().contiguous()}
+        L.prepare_weight(self._folded["Wf"])
+        return self._folded
+
+    def iterate_folded(self, x, n_iter=3):
+        """iterate() for the shared init through the folded affine map (one GEMM): same state up to FP32 rounding."""
+        if self.training:
+            raise L.GaitLibraryError("Regressor kernels implement eval() semantics (dropout = identity); call .eval()")
+        fk, pk = self.fold(n_iter), self._prepare()
+        x = L.f32(x, "x")
+        if x.dim() != 2 or x.shape[1] != pk["din"]:
+            raise ValueError(f"x must be (N,{pk['din']}), got {tuple(x.shape)}")
+        F = x.shape[0]
+        state = torch.empty(F, _STATE_LD, device=x.device)
+        nbytes = L.load().gait_hmr_folded_workspace_bytes(F)
+        ws = torch.empty(max(nbytes, 4) // 4, device=x.device)
+        L.call("gait_hmr_regressor_folded", L.ptr(x), x.stride(0), L.ptr(fk["Wf"]), L.ptr(fk["bf"]), L.ptr(state), F,
+               pk["din"], L.ptr(ws), nbytes, L.stream_ptr())
+        return state
 
     def iterate(self, x, init_pose=None, init_shape=None, init_cam=None, n_iter=3):
         """spin.py:244-265 - the MLP loop alone -> state (F,160) = [pose6d 144 | betas 10 | cam 3 | pad]."""
