@@ -16,6 +16,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _poison_uninitialised():
+    """GAITB200_TEST_POISON=1: every float tensor that torch.empty() hands out on a CUDA device is filled with NaN, so a
+    kernel that reads a buffer nobody wrote turns its outputs into NaN instead of depending on what ran before."""
+    import torch
+    real_empty = torch.empty
+
+    def empty(*a, **k):
+        t = real_empty(*a, **k)
+        if t.is_cuda and t.is_floating_point() and t.numel():
+            t.fill_(float("nan"))
+        return t
+
+    torch.empty = empty
+
+
+if os.environ.get("GAITB200_TEST_POISON") == "1":
+    _poison_uninitialised()
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():

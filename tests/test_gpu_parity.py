@@ -587,6 +587,25 @@ def test_head_c3_shard_sizes(S, lib_loaded):
         assert (got - ref32[key].double()).abs().max().item() <= tol + own, key
 
 
+def test_head_repeatable_bitwise(lib_loaded):
+    """Every kernel on the path is deterministic (fixed reduction orders, no atomics), so repeated steps on the same input
+    must agree bit for bit whatever else ran in between - a difference would be a synchronisation bug.  Timing and cache
+    state are perturbed between repetitions."""
+    head, _, _ = _heads()
+    junk = torch.randn(48 << 20, device="cuda")
+    for S, T_ in ((1, 16), (3, 5), (64, 16)):
+        feats = synthetic.make_features(S, T_, seed=77).cuda()
+        base = {k: v.clone() for k, v in head(feats).items()}
+        for rep in range(12):
+            if rep % 3 == 0:
+                junk.mul_(1.0001)                       # evicts L2
+            elif rep % 3 == 1:
+                torch.cuda.synchronize()
+            out = head(feats)
+            for k, v in out.items():
+                assert torch.equal(v, base[k]), (S, T_, rep, k)
+
+
 def test_head_long_clip_c4(lib_loaded):
     """BASELINE config 4: one long gait clip (S = 1); the recurrence runs T-1 dependent steps in the persistent kernel."""
     head, oracle, _ = _heads()

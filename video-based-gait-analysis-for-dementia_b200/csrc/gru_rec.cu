@@ -56,7 +56,13 @@ constexpr int TMEM_A = NBUF * NB;           // A operand ring: STAGES x 32 colum
 constexpr int TMEM_COLS = 512;
 static_assert(NBUF * NB + STAGES * BK <= 512, "tensor memory budget");
 constexpr int DRAIN_KB = 2;                 // k-blocks per promotion
-constexpr int NPROM = 256, NCONV = 256;
+#ifndef GAIT_GRU_CONV_GROUPS
+#define GAIT_GRU_CONV_GROUPS 2
+#endif
+constexpr int NGRP = GAIT_GRU_CONV_GROUPS;  // converter groups of 4 warps, taking k-blocks round-robin (3: 768 threads + setmaxnreg, measured 0.475 vs 0.483 ms)
+constexpr int NPROM = 256, NCONV = 128 * NGRP;
+// register budget after the setup with three groups (setmaxnreg), 768 threads x 80 at launch: 128 x 48 + 384 x 64 + 256 x 120
+constexpr int REGS_ISSUE = 48, REGS_CONV = 64, REGS_GATES = 120;
 constexpr int THREADS = 128 + NPROM + NCONV;
 constexpr int OFF_P = STAGES * STAGE;
 constexpr int OFF_BAR = OFF_P + P_FLOATS * 4;       // one partial-sum buffer (P_FREE handshake before it is rewritten)
@@ -115,7 +121,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(BAR(B_FULL_W + s), 3);           // one 32-row box per gate, each issued by its own lane
             mbar_init(BAR(B_FULL_H + s), 4);           // h and h_lo, two 32-sequence boxes each
-            mbar_init(BAR(B_CONV + s), NCONV / 64);       // one arrival per warp of the converter group that owns the k-block
+            mbar_init(BAR(B_CONV + s), 4);                // one arrival per warp of the converter group that owns the k-block
             mbar_init(BAR(B_EMPTY + s), 1);
         }
         for (int b = 0; b < NBUF; ++b) {
@@ -136,6 +142,8 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     cluster_sync_all();                                // peers' barriers exist before anyone arrives on them remotely
     const uint32_t tmem_d = *tmem_slot;
 
+    if (warp < 4) {
+    if (NGRP > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ISSUE));
     if (warp == 0) {
         // ------------------------------------------------------------ W_hh tile producer (independent of h)
         // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
@@ -249,7 +257,9 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
             ch += nchunks;
         }
-    } else if (warp >= 12 && warp < 20) {
+    }
+    } else if (warp >= 12) {
+        if (NGRP > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONV));
         // ------------------------------------------------------------ converters: two groups of 4 warps alternate k-blocks
         // W: lo tile only (the raw tile is the hi operand).  A: each thread moves one row of the stage's [h ; h_lo] tile
         // from shared memory into tensor memory (no arithmetic; TMEM lane = row, so a group needs all four warp quadrants).
@@ -259,7 +269,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         int it = 0;
         for (int step = first_gemm; step < T; ++step) {
             for (int kb = 0; kb < NKB; ++kb, ++it) {
-                if ((it & 1) != grp) continue;
+                if ((it % NGRP) != grp) continue;
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 uint8_t* st = gbase + s * STAGE;
@@ -297,7 +307,8 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (gt == 0) GRU_TRACE_KB(6);
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else {
+        if (NGRP > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GATES));
         // ------------------------------------------------------------ promotion + gates
         const int pt = threadIdx.x - 128;
         const int q = warp & 3;                            // TMEM lane quadrant of this warp

@@ -453,7 +453,9 @@ static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, co
     GAIT_REQUIRE(n_items < (1ll << 31), "smpl_lbs_tc: too many work items");
     const unsigned grid = (unsigned)std::min<int64_t>(n_items, n_sms);          // persistent: one CTA per SM
     CUtensorMap tmV;
-    GAIT_TRY(make_tensor_map_2d(&tmV, 8, v_posed, (uint64_t)(tiles * lbs::VT * 3 / 2), (uint64_t)F, (uint64_t)ldv * sizeof(float),
+    // inner extent = the 3V written floats (8-byte elements, V even): the padding of the last tile is zero-filled by TMA
+    // instead of being read from the (never written) tail of the v_posed rows
+    GAIT_TRY(make_tensor_map_2d(&tmV, 8, v_posed, (uint64_t)(V * 3 / 2), (uint64_t)F, (uint64_t)ldv * sizeof(float),
                                 lbs::VT * 3 / 2, lbs::FT, false));
 #define GAIT_LBS_LAUNCH(JX, MESH)                                                                                       \
     lbs::smpl_lbs_tc_kernel<JX, MESH><<<grid, lbs::THREADS3, lbs::SMEM3, stream>>>(                                       \

@@ -39,7 +39,7 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int BOX_ROWS = 32;               // rows per TMA box: the rows of a box are fetched serially, boxes in parallel
 constexpr int DRAIN_KB_LONG_K = 1;        // k-blocks accumulated in TMEM between promotions to FP32 registers when K >= 512 ...
 constexpr int DRAIN_KB_SHORT_K = 2;       // ... and for short contractions (few truncating accumulations anyway; the blend GEMM)
@@ -54,11 +54,15 @@ struct Cfg {
     static constexpr int P_TILE = BM * BK * 4;
     static constexpr int Q_TILE = BN * BK * 4;
     static constexpr int STAGE = P_TILE + 2 * Q_TILE;         // [P raw][Q raw = hi][Q lo]
-    static constexpr int STAGES = 4;                          // 4 x 32 KB (BN 64) or 4 x 48 KB (BN 128)
+#ifndef GAIT_BN64_STAGES
+#define GAIT_BN64_STAGES 4
+#define GAIT_BN64_NBUF 4
+#endif
+    static constexpr int STAGES = (BN <= 64) ? GAIT_BN64_STAGES : 4;   // x 32 KB (BN 64) or 4 x 48 KB (BN 128)
     static constexpr int STAGING = 8 * 32 * 20 * 4;          // 8 promotion warps x (32 rows x 16 columns, row stride 20)
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM = STAGES * STAGE + STAGING + BAR_BYTES + 1024;   // +1024 alignment slack
-    static constexpr int NBUF = (BN <= 64) ? 4 : 2;           // accumulator buffers (ring)
+    static constexpr int NBUF = (BN <= 64) ? GAIT_BN64_NBUF : 2;   // accumulator buffers (ring)
     static constexpr int TMEM_P0 = NBUF * BN;                 // first column of the P operand ring
     static constexpr int P_COLS = 2 * BK;                     // per stage: [hi 32 | lo 32]
     static constexpr int TMEM_COLS = 512;                     // NBUF * BN + STAGES * P_COLS = 512
