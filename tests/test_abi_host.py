@@ -182,3 +182,27 @@ def test_state_dict_keys_match_reference_layout(smpl_data):
     assert {"gru.weight_ih_l0", "gru.weight_hh_l1_reverse", "linear.weight"} <= set(enc.state_dict().keys())
     assert tuple(mine.smpl.joint_map.tolist()) == tuple(OS.SMPL(smpl_data).joint_map.tolist())
     assert PS.SMPL.extra is True and PS.SMPL.kinectv2 is True
+
+
+def test_kinect_db_writer_format(tmp_path):
+    """the joblib database of batch_generation.py:226-283 / doc/batch_generation.md - keys, dtypes, shapes,
+    per-frame video names, shard naming and the reference's rule for cutting shards."""
+    import joblib
+    import numpy as np
+    from gaitb200.postproc import KinectDbWriter
+    rng = np.random.default_rng(0)
+    vids = [(f"clip{i}.mp4", rng.standard_normal((3 + i, 25, 3)), rng.standard_normal((3 + i, 4))) for i in range(5)]
+    w = KinectDbWriter(str(tmp_path / "db.json"), max_videos=2, min_tail=1)
+    for i, (name, j, b) in enumerate(vids):
+        w.add(name, torch.from_numpy(j) if i % 2 else j.reshape(-1, 75), b, videos_left=len(vids) - 1 - i)
+    files = w.close()
+    assert [f.rsplit("/", 1)[1] for f in files] == ["db_0.json", "db_1.json"]     # cut before clip2; before clip4 only 1 video remains
+    dbs = [joblib.load(f) for f in files]
+    assert all(set(d) == {"vid_name", "bbox", "joints3D"} for d in dbs)
+    assert dbs[0]["joints3D"].shape == (3 + 4, 25, 3) and dbs[1]["joints3D"].shape == (5 + 6 + 7, 25, 3)
+    assert dbs[0]["joints3D"].dtype == np.float32 and dbs[0]["bbox"].dtype == np.float32 and dbs[0]["bbox"].shape == (7, 4)
+    assert list(dbs[0]["vid_name"]) == ["clip0"] * 3 + ["clip1"] * 4
+    allj = np.concatenate([v[1] for v in vids]).astype(np.float32)
+    assert np.array_equal(np.concatenate([d["joints3D"] for d in dbs]), allj)
+    with pytest.raises(ValueError):
+        KinectDbWriter(str(tmp_path / "db.pkl"))

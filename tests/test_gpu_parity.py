@@ -558,28 +558,34 @@ def test_head_joints_only_c5(lib_loaded):
         assert maxerr(b["kp_2d"], ref["kp_2d"]) <= TOL_2D
 
 
-def _oracle_fp64(oracle, feats):
-    """The same oracle evaluated in FP64 (its few in-line constants follow the default dtype)."""
+def _oracle_chunked(oracle, feats, fp64=False, chunk=128):
+    """The oracle on blocks of `chunk` sequences (they are independent; bounds host memory at 8192 frames), optionally
+    evaluated in FP64 (its few in-line constants follow the default dtype)."""
     import copy
-    o64 = copy.deepcopy(oracle).double()
-    torch.set_default_dtype(torch.float64)
+    o = copy.deepcopy(oracle).double() if fp64 else oracle
+    parts = []
+    if fp64:
+        torch.set_default_dtype(torch.float64)
     try:
-        return o64(feats.double())
+        for s0 in range(0, feats.shape[0], chunk):
+            x = feats[s0:s0 + chunk]
+            parts.append(o(x.double() if fp64 else x))
     finally:
         torch.set_default_dtype(torch.float32)
+    return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
 
 
-@pytest.mark.parametrize("S", [100, 200])
+@pytest.mark.parametrize("S", [100, 200, 512])
 def test_head_c3_shard_sizes(S, lib_loaded):
     """BASELINE config 3 shards (128 / 256 / 512 sequences per GPU): 100 sequences run the persistent recurrence as two
-    64-sequence launches, 200 take the per-step path.  Over thousands of frames the FP32 oracle's own rounding reaches the
+    64-sequence launches, 200 and 512 (the 2-GPU shard, 8192 frames) take the per-step path.  Over thousands of frames the FP32 oracle's own rounding reaches the
     rotation tolerance on the worst-conditioned frame (6-D vectors with a short first column; measured 9.7e-6 at S = 100
     between the oracle in FP32 and in FP64), so the bound is anchored on the exact value: the CUDA path is within the stated
     tolerance of the FP64 evaluation, and within tolerance + the oracle's own FP32 deviation of the FP32 oracle."""
     head, oracle, _ = _heads()
     feats = synthetic.make_features(S, 16, seed=9)
     out = head(feats.cuda())
-    ref32, ref64 = oracle(feats), _oracle_fp64(oracle, feats)
+    ref32, ref64 = _oracle_chunked(oracle, feats), _oracle_chunked(oracle, feats, fp64=True)
     for key, tol in (("rotmat", TOL_R), ("verts", TOL_V), ("kp_3d", TOL_V), ("kinect25", TOL_V), ("kp_2d", TOL_2D), ("theta", TOL_AA)):
         got = out[key].cpu().double()
         own = (ref32[key].double() - ref64[key]).abs().max().item()
@@ -606,10 +612,12 @@ def test_head_repeatable_bitwise(lib_loaded):
                 assert torch.equal(v, base[k]), (S, T_, rep, k)
 
 
-def test_head_long_clip_c4(lib_loaded):
-    """BASELINE config 4: one long gait clip (S = 1); the recurrence runs T-1 dependent steps in the persistent kernel."""
+@pytest.mark.parametrize("T_", [300, 900])
+def test_head_long_clip_c4(T_, lib_loaded):
+    """BASELINE config 4: one long gait clip (S = 1, up to 900 frames); the recurrence runs T-1 dependent steps in the
+    persistent kernel."""
     head, oracle, _ = _heads()
-    feats = synthetic.make_features(1, 300, seed=5)
+    feats = synthetic.make_features(1, T_, seed=5)
     out = head(feats.cuda())
     _check_head(out, oracle(feats))
 

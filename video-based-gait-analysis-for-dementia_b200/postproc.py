@@ -99,3 +99,52 @@ def convert_crop_coords_to_orig_img(bbox, keypoints, crop_size):
     L.call("gait_crop_coords_to_orig_img", L.ptr(b), int(b.dtype == torch.float64), b.stride(0), L.ptr(k), L.ptr(out),
            k.shape[0], k.shape[1], k.shape[2], float(crop_size), L.stream_ptr())
     return out.cpu().numpy() if was_np else out
+
+
+class KinectDbWriter:
+    """The Kinect-25 database batch_generation.py writes (batch_generation.py:226-238,262-283; doc/batch_generation.md:6-10):
+    a joblib dump of {'vid_name': (N,) str, 'bbox': (N,4) float32, 'joints3D': (N,25,3) float32}, one entry per frame in
+    temporal order, split into `<stem>_<k>.json` shards every `max_videos` videos (the reference's MAX_VID) with the
+    remainder in the last shard.  `add` accepts the head's `kinect25` output as a CUDA tensor (one device-to-host copy per
+    video) or a numpy array; this is host-side data-format code, no arithmetic."""
+
+    def __init__(self, outpath: str, max_videos: int = 300, min_tail: int = 10):
+        if not outpath.endswith(".json"):
+            raise ValueError("outpath must end with .json (batch_generation.py:235)")
+        self.outpath, self.max_videos, self.min_tail = outpath, int(max_videos), int(min_tail)
+        self._db = {"vid_name": [], "bbox": [], "joints3D": []}
+        self._videos = 0
+        self.files = []
+
+    def add(self, vid_name: str, joints3d, bbox, videos_left: int | None = None):
+        """One video: joints3d (frames,25,3) [any shape with frames*75 elements], bbox (frames,4).  `videos_left`: how many
+        videos follow (the reference only cuts a shard when more than `min_tail` remain)."""
+        if torch.is_tensor(joints3d):
+            joints3d = joints3d.detach().to("cpu", torch.float32).numpy()
+        bbox = np.asarray(bbox.detach().cpu().numpy() if torch.is_tensor(bbox) else bbox)
+        n = bbox.reshape(-1, 4).shape[0]
+        j = np.asarray(joints3d).reshape(n, 25, 3)
+        if self._videos and self._videos % self.max_videos == 0 and (videos_left is None or videos_left + 1 > self.min_tail):
+            self._flush()
+        self._db["vid_name"].extend([vid_name.split(".")[0]] * n)
+        self._db["bbox"].append(bbox.reshape(n, 4))
+        self._db["joints3D"].append(j)
+        self._videos += 1
+
+    def _flush(self):
+        import joblib
+        if not self._db["vid_name"]:
+            return None
+        db = {"vid_name": np.array(self._db["vid_name"]),
+              "bbox": np.concatenate(self._db["bbox"], axis=0).astype(np.float32),
+              "joints3D": np.concatenate(self._db["joints3D"], axis=0).astype(np.float32)}
+        path = self.outpath[:-5] + f"_{len(self.files)}.json"
+        joblib.dump(db, path)
+        self.files.append(path)
+        self._db = {"vid_name": [], "bbox": [], "joints3D": []}
+        return path
+
+    def close(self):
+        """Write the remaining frames; returns the list of files written."""
+        self._flush()
+        return self.files
