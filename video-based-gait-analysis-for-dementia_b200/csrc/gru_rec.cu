@@ -56,22 +56,27 @@ constexpr int TMEM_A = NBUF * NB;           // A operand ring: STAGES x 32 colum
 constexpr int TMEM_COLS = 512;
 static_assert(NBUF * NB + STAGES * BK <= 512, "tensor memory budget");
 constexpr int DRAIN_KB = 2;                 // k-blocks per promotion
-#ifndef GAIT_GRU_CONV_GROUPS
-#define GAIT_GRU_CONV_GROUPS 2
-#endif
-constexpr int NGRP = GAIT_GRU_CONV_GROUPS;  // converter groups of 4 warps, taking k-blocks round-robin (3: 768 threads + setmaxnreg, measured 0.475 vs 0.483 ms)
+constexpr int NGRP = 2;                     // converter groups of 4 warps alternating k-blocks (a third group: 768 threads with
+                                            // setmaxnreg, 0.475 vs 0.483 ms - not kept; it would also need its own barrier split)
 constexpr int NPROM = 256, NCONV = 128 * NGRP;
-// register budget after the setup with three groups (setmaxnreg), 768 threads x 80 at launch: 128 x 48 + 384 x 64 + 256 x 120
-constexpr int REGS_ISSUE = 48, REGS_CONV = 64, REGS_GATES = 120;
 constexpr int THREADS = 128 + NPROM + NCONV;
 constexpr int OFF_P = STAGES * STAGE;
 constexpr int OFF_BAR = OFF_P + P_FLOATS * 4;       // one partial-sum buffer (P_FREE handshake before it is rewritten)
-constexpr int SMEM = OFF_BAR + 256 + 1024;  // + barriers + alignment slack
+constexpr int BAR_AREA = 384;               // barriers (8 B each) + the TMEM base slot in the last 8 bytes
+constexpr int SMEM = OFF_BAR + BAR_AREA + 1024;  // + barriers + alignment slack
 static_assert(SMEM <= 232448, "shared memory budget");
 
-enum : int { B_FULL_W = 0, B_FULL_H = STAGES, B_CONV = 2 * STAGES, B_EMPTY = 3 * STAGES, B_ACC_FULL = 4 * STAGES,
-             B_ACC_EMPTY = 4 * STAGES + NBUF, B_P_READY = 4 * STAGES + 2 * NBUF, B_P_FREE = 4 * STAGES + 2 * NBUF + 1, B_COUNT = 4 * STAGES + 2 * NBUF + 2 };
-static_assert(B_COUNT * 8 <= 240, "barrier area");
+// "Data landed" barriers exist twice per stage, used by alternate fills of the stage (fill k -> barrier k & 1, phase
+// k >> 1).  A converter group only handles every NGRP-th k-block; with 5 stages and 2 groups it sees every OTHER fill of a
+// stage, and a parity wait on a barrier whose phases it skips would also pass while the fill in between is still
+// pending (try_wait.parity cannot tell phase k from phase k - 2).  With the split each group waits on every phase of the
+// barriers it uses.  All other barriers are waited on by warps that see each of their phases.
+enum : int { B_FULL_W = 0, B_FULL_H = 2 * STAGES, B_CONV = 4 * STAGES, B_EMPTY = 5 * STAGES, B_ACC_FULL = 6 * STAGES,
+             B_ACC_EMPTY = 6 * STAGES + NBUF, B_P_READY = 6 * STAGES + 2 * NBUF, B_P_FREE = 6 * STAGES + 2 * NBUF + 1, B_COUNT = 6 * STAGES + 2 * NBUF + 2 };
+static_assert(B_COUNT * 8 <= BAR_AREA - 8, "barrier area");
+// index of the landed-barrier and the parity to wait for, for the it-th k-block of the launch
+__device__ __forceinline__ int full_slot(int it) { return it % STAGES + STAGES * ((it / STAGES) & 1); }
+__device__ __forceinline__ uint32_t full_parity(int it) { return (uint32_t)((it / STAGES) >> 1) & 1u; }
 constexpr int FLAG_STRIDE = 32;             // words between the step flags of consecutive CTAs (one 128-byte line each)
 static_assert(KG == 2, "flag polling reads the two step flags of a cluster");
 static_assert(UPC == BK, "one k-block of h = the units of exactly one cluster (flag indexing)");
@@ -107,7 +112,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + OFF_BAR;
     auto BAR = [&](int i) { return bars + 8u * i; };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + OFF_BAR + 240);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + OFF_BAR + BAR_AREA - 8);
     float* P = reinterpret_cast<float*>(gbase + OFF_P);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,8 +124,10 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(BAR(B_FULL_W + s), 3);           // one 32-row box per gate, each issued by its own lane
-            mbar_init(BAR(B_FULL_H + s), 4);           // h and h_lo, two 32-sequence boxes each
+            for (int j = 0; j < 2; ++j) {
+                mbar_init(BAR(B_FULL_W + s + j * STAGES), 3);       // one 32-row box per gate, each issued by its own lane
+                mbar_init(BAR(B_FULL_H + s + j * STAGES), 4);       // h and h_lo, two 32-sequence boxes each
+            }
             mbar_init(BAR(B_CONV + s), 4);                // one arrival per warp of the converter group that owns the k-block
             mbar_init(BAR(B_EMPTY + s), 1);
         }
@@ -142,8 +149,6 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     cluster_sync_all();                                // peers' barriers exist before anyone arrives on them remotely
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp < 4) {
-    if (NGRP > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_ISSUE));
     if (warp == 0) {
         // ------------------------------------------------------------ W_hh tile producer (independent of h)
         // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
@@ -159,8 +164,9 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                     const uint32_t ph = (my / STAGES) & 1;
                     mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
                     if (g == 0) GRU_TRACE_KB(0);
-                    mbar_arrive_expect_tx(BAR(B_FULL_W + s), G_TILE);
-                    tma_load_2d(base + s * STAGE + A_TILE + g * G_TILE, &tmW, k0 + kb * BK, g * H + u0, BAR(B_FULL_W + s));
+                    const uint32_t fb = BAR(B_FULL_W + full_slot(my));
+                    mbar_arrive_expect_tx(fb, G_TILE);
+                    tma_load_2d(base + s * STAGE + A_TILE + g * G_TILE, &tmW, k0 + kb * BK, g * H + u0, fb);
                 }
                 __syncwarp();
                 it += min(2, NKB - kb0);
@@ -205,11 +211,12 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                     const uint32_t ph = (my / STAGES) & 1;
                     mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
                     if ((lane & 3) == 0) GRU_TRACE_KB(1);
-                    mbar_arrive_expect_tx(BAR(B_FULL_H + s), H_TILE / 2);
+                    const uint32_t fb = BAR(B_FULL_H + full_slot(my));
+                    mbar_arrive_expect_tx(fb, H_TILE / 2);
                     const uint32_t dst = base + s * STAGE + part * H_TILE + half * (H_TILE / 2);
-                    if (part) tma_load_3d(dst, &tmL, k0 + kb * BK, lslot, half * (SB / 2), BAR(B_FULL_H + s));
-                    else if (step == 0) tma_load_3d(dst, &tmH0, k0 + kb * BK, 0, half * (SB / 2), BAR(B_FULL_H + s));
-                    else tma_load_3d(dst, &tmY, k0 + kb * BK, tp, half * (SB / 2), BAR(B_FULL_H + s));
+                    if (part) tma_load_3d(dst, &tmL, k0 + kb * BK, lslot, half * (SB / 2), fb);
+                    else if (step == 0) tma_load_3d(dst, &tmH0, k0 + kb * BK, 0, half * (SB / 2), fb);
+                    else tma_load_3d(dst, &tmY, k0 + kb * BK, tp, half * (SB / 2), fb);
                 }
                 __syncwarp();
                 it += min(2, NKB - kb0);
@@ -257,9 +264,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
             ch += nchunks;
         }
-    }
-    } else if (warp >= 12) {
-        if (NGRP > 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONV));
+    } else if (warp >= 12 && warp < 20) {
         // ------------------------------------------------------------ converters: two groups of 4 warps alternate k-blocks
         // W: lo tile only (the raw tile is the hi operand).  A: each thread moves one row of the stage's [h ; h_lo] tile
         // from shared memory into tensor memory (no arithmetic; TMEM lane = row, so a group needs all four warp quadrants).
@@ -271,12 +276,11 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             for (int kb = 0; kb < NKB; ++kb, ++it) {
                 if ((it % NGRP) != grp) continue;
                 const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
                 uint8_t* st = gbase + s * STAGE;
                 const float4* w_hi = reinterpret_cast<const float4*>(st + A_TILE) + gt;
                 float4* w_lo = reinterpret_cast<float4*>(st + A_TILE + W_TILE) + gt;
                 constexpr int NW = W_TILE / 16 / 128;                 // 6
-                mbar_wait(BAR(B_FULL_W + s), ph);
+                mbar_wait(BAR(B_FULL_W + full_slot(it)), full_parity(it));
                 if (gt == 0) GRU_TRACE_KB(4);
                 float4 v[NW];
 #pragma unroll
@@ -284,7 +288,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
 #pragma unroll
                 for (int i = 0; i < NW; ++i)
                     w_lo[i * 128] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
-                mbar_wait(BAR(B_FULL_H + s), ph);
+                mbar_wait(BAR(B_FULL_H + full_slot(it)), full_parity(it));
                 if (gt == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
                 {
                     const float4* hrow = reinterpret_cast<const float4*>(st + gt * (BK * 4));
@@ -307,8 +311,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 if (gt == 0) GRU_TRACE_KB(6);
             }
         }
-    } else {
-        if (NGRP > 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GATES));
+    } else if (warp >= 4 && warp < 12) {
         // ------------------------------------------------------------ promotion + gates
         const int pt = threadIdx.x - 128;
         const int q = warp & 3;                            // TMEM lane quadrant of this warp

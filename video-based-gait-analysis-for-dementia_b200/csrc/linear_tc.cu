@@ -67,6 +67,9 @@ struct Cfg {
     static constexpr int P_COLS = 2 * BK;                     // per stage: [hi 32 | lo 32]
     static constexpr int TMEM_COLS = 512;                     // NBUF * BN + STAGES * P_COLS = 512
     static_assert(NBUF * BN + STAGES * P_COLS <= 512, "tensor memory budget");
+    // producers, converter groups and MMA issuers each come in pairs that alternate k-blocks / chunks; with an even number of
+    // stages and accumulator buffers every warp always returns to the same stages / buffers and sees each barrier phase
+    static_assert(STAGES % 2 == 0 && NBUF % 2 == 0, "stage and accumulator rings must be even");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -531,9 +534,20 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
         const char* d = getenv("GAITB200_TC_DRAIN");          // experiment knob: k-blocks per promotion
         drain_override = d ? atoi(d) : 0;
     }
+    // k-blocks per promotion.  Two only when every work item has an even number of k-blocks: the two MMA-issuing warps own
+    // alternate accumulator chunks, and only then does a chunk always cover the same pair of pipeline stages, so that each
+    // issuer waits on every phase of the "converted" barriers of its stages (a parity wait on a barrier whose phases a warp
+    // skips could pass one fill early).  One k-block per chunk keeps chunk and stage counters in step for any length.
+    int drain = (K >= 512) ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K;
+    if (drain_override > 0) drain = drain_override;
+    if (drain == 2 && ((kb_per_split & 1) || (nkb & 1))) drain = 1;
+    if (drain != 1 && drain != 2) {
+        set_error("linear(tc): GAITB200_TC_DRAIN must be 1 or 2");
+        return GAIT_ERR_INVALID;
+    }
     gemm_tf32x3_kernel<BN, QLO><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
                                                                      transposed, kb_per_split, split_stride, tiles_p, splits,
-                                                                     n_items, mode, drain_override > 0 ? drain_override : (K >= 512 ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K), g_trace);
+                                                                     n_items, mode, drain, g_trace);
     return check_launch("linear(tf32x3 tcgen05)");
 }
 
