@@ -67,6 +67,14 @@ int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, c
                      int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int splits,
                      int64_t split_stride, cudaStream_t stream);
 int linear_path();
+// Call-site knob of the tensor-core GEMM: k-blocks (32 k) accumulated in tensor memory between promotions to FP32 registers
+// (0 = by K: 1 for K >= 512, else 2).  1 is the more accurate, 2 the faster setting (see linear_tc.cu).
+extern thread_local int g_linear_promote_kb;
+struct LinearPromote {
+    int prev;
+    explicit LinearPromote(int kb) : prev(g_linear_promote_kb) { g_linear_promote_kb = kb; }
+    ~LinearPromote() { g_linear_promote_kb = prev; }
+};
 // tma.cu: CUtensorMap (128-byte opaque) builder
 int make_tensor_map_2d(void* map, int elem_bytes, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t row_stride_bytes,
                        uint32_t box0, uint32_t box1, bool swizzle128);

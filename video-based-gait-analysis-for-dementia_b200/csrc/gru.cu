@@ -91,7 +91,13 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
     float* gh = gi + S * T * 3 * H;
     const int64_t F = S * T;
     // gi = x . W_ih^T + b_ih for every frame
-    GAIT_TRY(linear_launch(x, ldx, W_ih, I, b_ih, nullptr, 0, gi, 3 * H, F, 3 * H, I, st));
+    {
+        // the projection feeds the gates' sigmoid / tanh and a contractive recurrence: 64-deep partial sums are accurate
+        // enough here (encoder output rms error 8.8e-8 against FP64, FP32 torch 5.8e-8; 4.8e-8 with 32-deep sums) and the
+        // GEMM is 10 % faster than with 32-deep ones
+        LinearPromote promote(2);
+        GAIT_TRY(linear_launch(x, ldx, W_ih, I, b_ih, nullptr, 0, gi, 3 * H, F, 3 * H, I, st));
+    }
     // whole recurrence in one persistent cluster kernel (gru_rec.cu) when the shape allows;
     // GAITB200_GRU_PATH=1 forces the per-step path below, =2 makes ineligibility an error
     static int gru_path = -1;

@@ -538,7 +538,7 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
     // alternate accumulator chunks, and only then does a chunk always cover the same pair of pipeline stages, so that each
     // issuer waits on every phase of the "converted" barriers of its stages (a parity wait on a barrier whose phases a warp
     // skips could pass one fill early).  One k-block per chunk keeps chunk and stage counters in step for any length.
-    int drain = (K >= 512) ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K;
+    int drain = g_linear_promote_kb > 0 ? g_linear_promote_kb : ((K >= 512) ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K);
     if (drain_override > 0) drain = drain_override;
     if (drain == 2 && ((kb_per_split & 1) || (nkb & 1))) drain = 1;
     if (drain != 1 && drain != 2) {
@@ -552,6 +552,8 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
 }
 
 }  // namespace tc
+
+thread_local int g_linear_promote_kb = 0;
 
 // debug: per-k-block pipeline timestamps of CTA 0 (trace[kb*4 + {stage free, data landed, converted, MMAs issued}])
 void linear_tc_set_trace(unsigned long long* p) { tc::g_trace = p; }
