@@ -247,9 +247,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const int kb0 = z * kb_per_split;                                                                                 \
         const int nkb = min(kb_per_split, nkb_total - kb0);                                                               \
         const int nchunks = (nkb + drain_kb - 1) / drain_kb;                                                              \
-        (void)pt; (void)p0; (void)q0; (void)kb0; (void)nchunks; (void)ch;
+        /* ring slots this item takes: with two k-blocks per chunk an odd count is padded by one EMPTY slot that only     \
+           passes through the barriers, so that `it` stays 2 * ch and every issuer keeps its pair of stages */            \
+        const int nslots = (drain_kb == 2) ? (nkb + 1) & ~1 : nkb;                                                        \
+        (void)pt; (void)p0; (void)q0; (void)kb0; (void)nchunks; (void)ch; (void)nslots;
 #define ITEM_LOOP_END                                                                                                     \
-        it += nkb;                                                                                                        \
+        it += nslots;                                                                                                     \
         ch += nchunks;                                                                                                    \
     }
     if (warp < 4) {
@@ -262,13 +265,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             // fetched one after the other, boxes issued by different lanes / warps proceed in parallel.
             const int par = warp == 0 ? 0 : 1;
             constexpr int PB = BM / BOX_ROWS, QB = BN / BOX_ROWS;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nslots; ++kb) {
                 if (((it + kb) & 1) != par) continue;
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
                 const uint32_t st = base + s * cfg::STAGE;
-                if (lane < PB + (QLO ? 2 : 1) * QB) {
+                if (kb >= nkb) {                                            // padding slot: complete the phase, load nothing
+                    if (lane < PB + (QLO ? 2 : 1) * QB) mbar_arrive(BAR(B_FULL + s));
+                } else if (lane < PB + (QLO ? 2 : 1) * QB) {
                     if (trace && blockIdx.x == 0 && lane == 0 && it + kb < 64) trace[(it + kb) * 4 + 0] = clock64();
                     mbar_arrive_expect_tx(BAR(B_FULL + s), BOX_ROWS * BK * 4);
                     if (lane < PB) tma_load_2d(st + lane * (BOX_ROWS * BK * 4), &tmP, (kb0 + kb) * BK, p0 + lane * BOX_ROWS, BAR(B_FULL + s));
@@ -283,12 +288,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             // ------------------------------------------------------------ MMA issuers (warp-uniform loop, one lane issues)
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const int par = warp == 1 ? 0 : 1;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nslots; ++kb) {
                 const int cg = ch + kb / drain_kb, buf = cg % cfg::NBUF, use = cg / cfg::NBUF;
                 if ((cg & 1) != par) continue;
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 const bool chunk_start = (kb % drain_kb) == 0;
+                if (kb >= nkb) {                                            // padding slot: hand the stage straight back
+                    mbar_wait(BAR(B_CONV + s), ph);
+                    if (elect_one()) umma_commit(BAR(B_EMPTY + s));
+                    __syncwarp();
+                    continue;
+                }
                 if (chunk_start && use >= 1) mbar_wait(BAR(B_ACC_EMPTY + buf), (use - 1) & 1);
                 mbar_wait(BAR(B_CONV + s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -329,11 +340,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             const int grp = (warp - 12) >> 2;
             const int quad = warp & 3;                               // TMEM lane quadrant this warp may write
             const int gt = quad * 32 + lane;                         // thread in the group = P tile row = TMEM lane
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nslots; ++kb) {
                 if (((it + kb) & 1) != grp) continue;
                 const int s = (it + kb) % STAGES;
                 const uint32_t ph = ((it + kb) / STAGES) & 1;
                 mbar_wait(BAR(B_FULL + s), ph);
+                if (kb >= nkb) {                                            // padding slot
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(B_CONV + s));
+                    continue;
+                }
                 if (trace && blockIdx.x == 0 && gt == 0 && it + kb < 64) trace[(it + kb) * 4 + 1] = clock64();
                 uint8_t* st = gbase + s * cfg::STAGE;
                 // P: this thread's row (8 x 16 bytes, un-swizzled while reading) -> tensor memory [hi 32 | lo 32]
@@ -534,13 +550,12 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
         const char* d = getenv("GAITB200_TC_DRAIN");          // experiment knob: k-blocks per promotion
         drain_override = d ? atoi(d) : 0;
     }
-    // k-blocks per promotion.  Two only when every work item has an even number of k-blocks: the two MMA-issuing warps own
-    // alternate accumulator chunks, and only then does a chunk always cover the same pair of pipeline stages, so that each
-    // issuer waits on every phase of the "converted" barriers of its stages (a parity wait on a barrier whose phases a warp
-    // skips could pass one fill early).  One k-block per chunk keeps chunk and stage counters in step for any length.
+    // k-blocks per promotion.  The two MMA-issuing warps own alternate accumulator chunks; each must wait on every phase of
+    // the "converted" barriers of the stages it uses (a parity wait on a barrier whose phases a warp skips could pass one
+    // fill early), so a chunk always has to cover the same stages: with one k-block per chunk chunk and stage counters stay
+    // in step by construction, with two the kernel pads an item with an odd number of k-blocks by one empty ring slot.
     int drain = g_linear_promote_kb > 0 ? g_linear_promote_kb : ((K >= 512) ? DRAIN_KB_LONG_K : DRAIN_KB_SHORT_K);
     if (drain_override > 0) drain = drain_override;
-    if (drain == 2 && ((kb_per_split & 1) || (nkb & 1))) drain = 1;
     if (drain != 1 && drain != 2) {
         set_error("linear(tc): GAITB200_TC_DRAIN must be 1 or 2");
         return GAIT_ERR_INVALID;
