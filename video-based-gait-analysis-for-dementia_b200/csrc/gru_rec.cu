@@ -411,10 +411,10 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                                 (1.f - z3) * n3 + z3 * hp.w);
             }
             hp = h;
+            // what the next step of other CTAs reads (h_t and its lo part) goes out first and is published; the outputs nobody
+            // inside the kernel reads (h_t + residual, h_n) are stored after the flag so that they are off the critical path
             if (act) {
                 *reinterpret_cast<float4*>(y + f * ldy + unit) = h;
-                if (out) *reinterpret_cast<float4*>(out + f * ldout + unit) = f4_add(h, rs);
-                if (hn && step == T - 1) *reinterpret_cast<float4*>(hn + (int64_t)seq * H + unit) = h;
                 if (step < T - 1)          // lo half of the next step's A operand (hi = h itself, read truncated)
                     *reinterpret_cast<float4*>(hlo + ((int64_t)seq * 2 + (step & 1)) * H + unit) =
                         make_float4(tf32_lo(h.x), tf32_lo(h.y), tf32_lo(h.z), tf32_lo(h.w));
@@ -429,6 +429,10 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                         for (uint32_t rr = 0; rr < (uint32_t)KG; ++rr) mbar_arrive_remote_release(map_to_rank(BAR(B_P_FREE), rr));
                     }
                 }
+            }
+            if (act) {
+                if (out) *reinterpret_cast<float4*>(out + f * ldout + unit) = f4_add(h, rs);
+                if (hn && step == T - 1) *reinterpret_cast<float4*>(hn + (int64_t)seq * H + unit) = h;
             }
             if (pt == 0) GRU_TRACE_STEP(5);
             if (TRACE && trace && pt == 0 && step == 3) trace[1024 + blockIdx.x * 2] = global_timer_ns();
