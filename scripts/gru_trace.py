@@ -31,13 +31,13 @@ L.call("gait_debug_gru_trace", None)
 t = tr.cpu()
 st = t[:256].view(32, 8)
 t0 = int(st[0, 5])
-print("step: bar_wait_start bar_passed first_h_landed last_mma_issued drained P_ready stored | step period (cycles)")
+print("step: bar_wait_start bar_passed first_h_landed last_mma_issued drained P_ready gates_done stored | step period (cycles)")
 prev = None
 for s in range(T):
-    v = [int(st[s, i]) - t0 if int(st[s, i]) else 0 for i in (6, 0, 1, 2, 3, 4, 5)]
-    per = "" if prev is None else v[6] - prev
+    v = [int(st[s, i]) - t0 if int(st[s, i]) else 0 for i in (6, 0, 1, 2, 3, 4, 7, 5)]
+    per = "" if prev is None else v[7] - prev
     print(f"{s:3d} " + " ".join(f"{a:9d}" for a in v) + f"   {per}")
-    prev = v[6]
+    prev = v[7]
 kb = t[256:768].view(64, 8)
 k0 = int(kb[0, 0])
 print("step 2 k-blocks (cycles; + = relative to W issue): W_issue | h_issue+ convW_start+ convH_start+ conv_done(warp12)+ mma:acc_free+ mma:conv_seen+ mma_issued+ | period")

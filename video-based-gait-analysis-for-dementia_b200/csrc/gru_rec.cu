@@ -411,6 +411,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                                 (1.f - z3) * n3 + z3 * hp.w);
             }
             hp = h;
+            if (pt == 0) GRU_TRACE_STEP(7);
             // what the next step of other CTAs reads (h_t and its lo part) goes out first and is published; the outputs nobody
             // inside the kernel reads (h_t + residual, h_n) are stored after the flag so that they are off the critical path
             if (act) {
