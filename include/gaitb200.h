@@ -130,7 +130,8 @@ int gait_relu(const float* x, float* y, int64_t n, gait_stream_t stream);
 /* state = [pose6d(144) | betas(10) | cam(3)] = 157 floats, stored with row stride 160.
  * W1x (Dh,Din) = fc1.weight[:, :Din];  W1s (Dh,160) = fc1.weight[:, Din:] zero padded;
  * W2 (Dh,Dh); Wd (157,Dh) = [decpose;decshape;deccam].weight; bd (157).
- * init (1,160) broadcast when init_rows==1, else (F,160).  state_out (F,160). */
+ * init (1,160) broadcast when init_rows==1, else (F,160).  state_out (F,160).  With a shared init the constant term
+ * init . W1s^T is computed once per call and folded into the bias of the x-part GEMM (iteration 0 then needs no state GEMM). */
 size_t gait_hmr_workspace_bytes(int64_t F, int64_t Dh);
 int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const float* W1s, const float* b1,
                        const float* W2, const float* b2, const float* Wd, const float* bd,

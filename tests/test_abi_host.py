@@ -72,7 +72,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.gait_smpl_lbs_pack_bytes(6890) == 54 * 24576 and lib.gait_smpl_lbs_aop_bytes(1024) == 128 * 18432
     assert lib.gait_linear(C.c_void_p(16), 4, C.c_void_p(16), 8, None, None, 0, C.c_void_p(16), 8, 2, 8, 8, None) == -1
     assert lib.gait_gru_workspace_bytes(64, 16, 2048) == (64 * 16 * 6144 + 4 * 64 * 6144) * 4 + 128 * (2048 // 16 + 2) + 2 * 64 * 2048 * 4   # + step flags, h_lo scratch
-    assert lib.gait_hmr_workspace_bytes(1024, 1024) == (3 * 1024 * 1024 + 6 * 1024 * 160) * 4
+    assert lib.gait_hmr_workspace_bytes(1024, 1024) == (3 * 1024 * 1024 + 6 * 1024 * 160 + 2 * 1024) * 4
     assert lib.gait_hmr_folded_workspace_bytes(1024) == 6 * 1024 * 160 * 4 and lib.gait_hmr_folded_workspace_bytes(0) == 0
     assert lib.gait_hmr_regressor_folded(None, 2048, None, None, None, 4, 2048, None, 0, None) == -1   # null pointers
     n0 = lib.gait_launch_count()

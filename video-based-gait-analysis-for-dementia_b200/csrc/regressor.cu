@@ -26,6 +26,34 @@ __global__ void broadcast_state_kernel(const float* __restrict__ init, int64_t i
     state[i] = v;
 }
 
+// Shared initial state (init_rows == 1): init.W1s^T is the same vector v for every frame, so it is computed once per call
+// (one warp per hidden unit) and carried by the bias: the x-part GEMM gets b1 + v and directly yields fc1 of iteration 0;
+// later iterations add state.W1s^T - v to it.  bias1 = [b1 + v | -v].
+// The same launch also broadcasts the initial state (blocks below `state_blocks`).
+__global__ void init_term_kernel(const float* __restrict__ W1s, const float* __restrict__ init, const float* __restrict__ b1,
+                                 float* __restrict__ bias1, int64_t Dh, float* __restrict__ state, int64_t F,
+                                 unsigned state_blocks) {
+    if (blockIdx.x < state_blocks) {
+        const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        if (i < F * kStateLd) {
+            const int c = (int)(i % kStateLd);
+            state[i] = (c < kState) ? init[c] : 0.f;
+        }
+        return;
+    }
+    const int64_t row = ((blockIdx.x - state_blocks) * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= Dh) return;
+    float v = 0.f;
+    for (int c = lane; c < kState; c += 32) v = fmaf(W1s[row * kStateLd + c], init[c], v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+        bias1[row] = b1[row] + v;
+        bias1[Dh + row] = -v;
+    }
+}
+
 constexpr int kDecSplits = 6;          // split-K of the 157-row decoder GEMM (only 24 output tiles otherwise)
 
 // state[f, c] += sum over split-K partials (partial 0 already holds bias); one thread per element
@@ -68,7 +96,7 @@ extern "C" {
 
 size_t gait_hmr_workspace_bytes(int64_t F, int64_t Dh) {
     if (F <= 0 || Dh <= 0) return 0;
-    return (size_t)(3 * F * Dh + kDecSplits * F * kStateLd) * sizeof(float);
+    return (size_t)(3 * F * Dh + kDecSplits * F * kStateLd + 2 * Dh) * sizeof(float);
 }
 
 size_t gait_hmr_folded_workspace_bytes(int64_t F) {
@@ -119,6 +147,8 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
     float* h1 = hx + F * Dh;
     float* h2 = h1 + F * Dh;
     float* dpart = h2 + F * Dh;                          // split-K partials of the decoder GEMM
+    float* bias1 = dpart + kDecSplits * F * kStateLd;    // [b1 + init.W1s^T | -init.W1s^T] when the init is shared
+    const bool shared_init = init_rows == 1;
     // decoder GEMM (F x 157 x Dh): few output tiles, so cut K across CTAs when the tensor-core path takes it
     int dsplits = 1;
     if (linear_path() != 1 && linear_tc_eligible(h2, Dh, Wd, Dh, F, kState, Dh)) {
@@ -126,14 +156,24 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
         dsplits = (int)std::min<int64_t>(kDecSplits, nkb);
         while (dsplits > 1 && ceil_div(nkb, ceil_div(nkb, dsplits)) != dsplits) --dsplits;
     }
-    broadcast_state_kernel<<<(unsigned)ceil_div(F * kStateLd, 256), 256, 0, st>>>(init, init_rows, state_out, F);
-    GAIT_TRY(check_launch("hmr broadcast_state"));
+    const unsigned state_blocks = (unsigned)ceil_div(F * kStateLd, 256);
+    if (shared_init && n_iter > 0) {
+        init_term_kernel<<<state_blocks + (unsigned)ceil_div(Dh * 32, 256), 256, 0, st>>>(W1s, init, b1, bias1, Dh, state_out,
+                                                                                             F, state_blocks);
+        GAIT_TRY(check_launch("hmr init_term + broadcast_state"));
+    } else {
+        broadcast_state_kernel<<<state_blocks, 256, 0, st>>>(init, init_rows, state_out, F);
+        GAIT_TRY(check_launch("hmr broadcast_state"));
+    }
     if (n_iter == 0) return GAIT_OK;
-    // iteration-invariant part of fc1
-    GAIT_TRY(linear_launch(x, ldx, W1x, Din, b1, nullptr, 0, hx, Dh, F, Dh, Din, st));
+    // iteration-invariant part of fc1 (with a shared init: all of fc1 for iteration 0)
+    GAIT_TRY(linear_launch(x, ldx, W1x, Din, shared_init ? bias1 : b1, nullptr, 0, hx, Dh, F, Dh, Din, st));
     for (int it = 0; it < n_iter; ++it) {
-        GAIT_TRY(linear_launch(state_out, kStateLd, W1s, kStateLd, nullptr, hx, Dh, h1, Dh, F, Dh, kStateLd, st));
-        GAIT_TRY(linear_launch(h1, Dh, W2, Dh, b2, nullptr, 0, h2, Dh, F, Dh, Dh, st));
+        const float* fc1 = h1;
+        if (shared_init && it == 0) fc1 = hx;
+        else GAIT_TRY(linear_launch(state_out, kStateLd, W1s, kStateLd, shared_init ? bias1 + Dh : nullptr, hx, Dh, h1, Dh, F, Dh,
+                                    kStateLd, st));
+        GAIT_TRY(linear_launch(fc1, Dh, W2, Dh, b2, nullptr, 0, h2, Dh, F, Dh, Dh, st));
         if (dsplits > 1) {
             GAIT_TRY(linear_tc_launch(h2, Dh, Wd, Dh, bd, nullptr, 0, dpart, kStateLd, F, kState, Dh, dsplits,
                                       F * kStateLd, st));
