@@ -543,6 +543,12 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
     // persistent CTAs, one per SM; balance the number of items per CTA
     const int per_cta = (int)ceil_div(n_items, n_sms);
     dim3 grid((unsigned)ceil_div(n_items, per_cta));
+    static int max_ctas = -1;                                     // experiment knob: fewer CTAs (is the operand stream limited
+    if (max_ctas < 0) {                                           // per SM or by the L2 as a whole?)
+        const char* e = getenv("GAITB200_TC_MAXCTAS");
+        max_ctas = e ? atoi(e) : 0;
+    }
+    if (max_ctas > 0 && (int)grid.x > max_ctas) grid.x = (unsigned)max_ctas;
     static int mode = -1, drain_override = 0;
     if (mode < 0) {
         const char* e = getenv("GAITB200_TC_MODE");
