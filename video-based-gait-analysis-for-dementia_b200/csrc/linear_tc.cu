@@ -514,9 +514,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------ host
-// tile_rows = BM for the 128-row operand, BN for the other one
-static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t K, int64_t ld, int tile_rows) {
-    const int box_rows = tile_rows == BM ? P_BOX : q_box(tile_rows);
+// box_rows: P_BOX for the 128-row operand, q_box(BN) for the other one (the kernel issues boxes of exactly these heights)
+static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
     return make_tensor_map_2d(m, /*elem_bytes=*/4, ptr, (uint64_t)K, (uint64_t)rows, (uint64_t)ld * sizeof(float), BK,
                               box_rows, /*swizzle128=*/true);
 }
@@ -630,23 +629,23 @@ int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, c
     const bool transposed = M <= 64 || (M < 128 && N >= 128);
     if (transposed) {
         const int bn = (M <= 64) ? 64 : 128;
-        GAIT_TRY(make_map(&tmP, W, N, K, ldw, BM));
-        GAIT_TRY(make_map(&tmQ, A, M, K, lda, bn));
+        GAIT_TRY(make_map(&tmP, W, N, K, ldw, P_BOX));
+        GAIT_TRY(make_map(&tmQ, A, M, K, lda, q_box(bn)));
         if (bn == 64)
             return launch<64, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
         return launch<128, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
     }
     const int bn = (ceil_div(M, BM) * ceil_div(N, 128) < 120 && N > 64) ? 64 : 128;
-    GAIT_TRY(make_map(&tmP, A, M, K, lda, BM));
+    GAIT_TRY(make_map(&tmP, A, M, K, lda, P_BOX));
     const float *Whi = nullptr, *Wlo = nullptr;
     if (find_prepared(W, (N - 1) * ldw + K, &Whi, &Wlo) && aligned16(Whi) && aligned16(Wlo)) {
-        GAIT_TRY(make_map(&tmQ, Whi, N, K, ldw, bn));          // the prepared hi array replaces the raw weights
-        GAIT_TRY(make_map(&tmQlo, Wlo, N, K, ldw, bn));
+        GAIT_TRY(make_map(&tmQ, Whi, N, K, ldw, q_box(bn)));          // the prepared hi array replaces the raw weights
+        GAIT_TRY(make_map(&tmQlo, Wlo, N, K, ldw, q_box(bn)));
         if (bn == 64)
             return launch<64, true>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
         return launch<128, true>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
     }
-    GAIT_TRY(make_map(&tmQ, W, N, K, ldw, bn));
+    GAIT_TRY(make_map(&tmQ, W, N, K, ldw, q_box(bn)));
     if (bn == 64)
         return launch<64, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
     return launch<128, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)M, (int)N, (int)K, 0, splits, split_stride, stream);
