@@ -5,23 +5,31 @@
 
 A step = one pass of the whole hot path (GRU temporal encoder -> 3-iteration HMR regressor ->
 rot6d->R -> SMPL blend shapes -> kinematic chain -> LBS of 6890 vertices -> joint regression ->
-Kinect-25 joints + weak-perspective projection + theta) over one batch of synthetic backbone
-features: BASELINE.json configs[1], 64 sequences x 16 frames PER GPU, full mesh output.
-Sequences are independent, so N GPUs run N shards with no data-path collective (weak scaling).
+Kinect-25 joints + weak-perspective projection + theta) over one batch of synthetic backbone features.
 
-Own arm (default): one JSON line with `value` (inputs resident in HBM, CUDA-graph replay, CUDA
-events per step, L2 flushed between steps, max over ranks), `e2e` (host pinned buffers -> H2D ->
-step -> D2H of every output, per step), `roofline` (LBS kernel: algorithmic bytes / measured
-kernel time vs MEASURED_PEAKS.json), per-stage timings, `cpu_baseline` (the CPU FP32 oracle on
-this box's cores, rank 0 at N=1), `clocks` (NVML samples during the timed region).
+  N = 1 : BASELINE.json configs[1] - 64 sequences x 16 frames on one B200, full mesh output.  The line also carries a
+          `configs` object with the other BASELINE configurations measured on this GPU: c3_n1 (all 1024 sequences of
+          configs[2] on one GPU = the denominator of strong scaling), c4 (one long clip, T = 16..900), c5 (joints-only),
+          c1 (1 x 16 frames, batch 1, CPU oracle and GPU), plus the J_regressor stage.
+  N > 1 : BASELINE.json configs[2] - 1024 sequences x 16 frames sharded by sequence (1024/N per GPU), with the one
+          exchange north_star names INSIDE the timed step: the final gather of meshes + Kinect-25 joints onto rank 0
+          (sharding.RootGather: skinning-kernel stores / copy-engine puts into the root's IPC-mapped buffer over NVLink, or
+          NCCL send/recv; the fastest of the candidates is the headline, all are reported).  scaling = "strong".
 
-Reference arm (`--impl reference`): the reference's own CPU FP32 path for the same config, i.e.
-the oracle restatement under oracle/ (the reference's model modules cannot be imported or
-installed here - SURVEY.md 8(c); its geometry/kp_utils/wrapper code is pinned by tests/golden).
+Own arm: one JSON line with `value` (inputs resident in HBM, CUDA-graph replay, CUDA events per step on the launching
+stream, L2 flushed between steps, max over ranks), `e2e` (host pinned buffers -> H2D -> step -> D2H of every output, per
+step, with the box's measured concurrent-D2H ceiling beside it), `roofline` (LBS kernel: algorithmic bytes / measured
+kernel time vs MEASURED_PEAKS.json), per-stage timings, `cpu_baseline` (the CPU FP32 oracle on this box's cores, rank 0
+at N=1), `clocks` (NVML samples during the timed region).
+
+Reference arm (`--impl reference`): the reference's own CPU FP32 path for the same config, i.e. the oracle restatement
+under oracle/ (the reference's model modules cannot be imported or installed here - SURVEY.md 8(c); its
+geometry/kp_utils/wrapper code is pinned by tests/golden).  At N>1 it runs all 1024 sequences of configs[2].
 """
 from __future__ import annotations
 
 import argparse
+import copy
 import json
 import os
 import sys
@@ -37,10 +45,13 @@ import torch  # noqa: E402
 
 METRIC = "smpl_regressed_frames_per_sec"
 UNIT = "frames/s"
+C3_SEQS = 1024                                                 # BASELINE configs[2]
 
 # algorithmic figures per frame (DESIGN.md "Measurement")
 LBS_BYTES_PER_FRAME = 6890 * 3 * 4 * 2 + 24 * 12 * 4          # v_posed in + verts out + A  = 166 512
 LBS_BYTES_ONCE = 6890 * 24 * 4                                 # lbs_weights, once per launch
+JREG_BYTES_PER_FRAME = lambda rows: 6890 * 3 * 4 + 12 * rows   # verts in + joints out         
+JREG_BYTES_ONCE = lambda rows: 6890 * 4 * rows                 # regressor rows, once per launch
 FLOPS_PER_FRAME = {"gru": 2 * 2 * 3 * 2048 * 2048, "regressor": 2 * (2048 * 1024 + 3 * (160 * 1024 + 1024 * 1024 + 157 * 1024)),
                    "blend": 2 * 218 * 20670}
 OUT_BYTES_PER_FRAME = (6890 * 3 + 29 * 3 + 29 * 2 + 25 * 3 + 85 + 24 * 9) * 4    # verts, kp_3d, kp_2d, kinect25, theta, rotmat
@@ -53,7 +64,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--seqs-per-gpu", type=int, default=64)
+    ap.add_argument("--seqs-per-gpu", type=int, default=None,
+                    help="default: 64 at N=1 (configs[1]); 1024/N at N>1 (configs[2])")
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--variant", choices=["sparse", "dense"], default="sparse",
                     help="synthetic SMPL weights: SMPL-like sparse (<=4 skin weights / vertex) or fully dense")
@@ -63,11 +75,18 @@ def parse_args():
                     help="opt-in: run the regressor loop as its folded affine map (Regressor.fold); not the headline")
     ap.add_argument("--slots", type=int, default=2, help="buffer sets for the pipelined end-to-end path")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--gather", choices=["none", "joints", "mesh"], default="none",
-                    help="NCCL all-gather of Kinect-25 joints (or joints+mesh) inside the timed step (N>1)")
+    ap.add_argument("--gather", choices=["auto", "none", "nccl", "peer-copy", "peer-store"], default="auto",
+                    help="N>1: how meshes + Kinect-25 joints reach rank 0 inside the timed step (auto = time the candidates, "
+                         "report all, headline = fastest)")
+    ap.add_argument("--chunks", type=int, default=0, help="N>1: sub-batches per step whose gather overlaps the next one's compute (0 = per mode)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extra-configs", action="store_true", help="N=1: skip the c3_n1 / c4 / c5 / c1 sub-records")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.seqs_per_gpu is None:
+        args.seqs_per_gpu = 64 if world == 1 else max(1, C3_SEQS // world)
+    return args
 
 
 def load_peaks():
@@ -79,7 +98,7 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def make_models(args, want_gpu: bool, want_oracle: bool):
+def make_models(args, want_gpu: bool, want_oracle: bool, **head_kw):
     from gaitb200 import synthetic
     smpl_data = synthetic.make_smpl_data(seed=0, variant=args.variant)
     mean = synthetic.make_mean_params()
@@ -88,8 +107,9 @@ def make_models(args, want_gpu: bool, want_oracle: bool):
     head = oracle = None
     if want_gpu:
         from gaitb200.head import GaitHead
-        head = GaitHead(smpl_data, mean, reg_state, gru_state, write_mesh=not getattr(args, "joints_only", False),
-                        fold_regressor=getattr(args, "fold_regressor", False)).cuda()
+        kw = dict(write_mesh=not getattr(args, "joints_only", False), fold_regressor=getattr(args, "fold_regressor", False))
+        kw.update(head_kw)
+        head = GaitHead(smpl_data, mean, reg_state, gru_state, **kw).cuda()
     if want_oracle:
         from oracle.head import GaitHeadOracle
         oracle = GaitHeadOracle(smpl_data, mean, reg_state, gru_state)
@@ -111,52 +131,65 @@ def time_oracle(oracle, feats, budget_s: float, min_runs: int = 1, max_runs: int
     return frames / best, runs, best
 
 
-def run_reference(args, rank: int):
+def run_reference(args, rank: int, world: int):
+    """The reference's CPU FP32 path (oracle port) on this arm's config: N=1 -> configs[1] (64 x 16), N>1 -> ALL 1024
+    sequences of configs[2], processed per step in 64-sequence blocks (the reference's own chunking, demo.py:149)."""
     if rank != 0:
         return
     from gaitb200 import synthetic
     _, oracle = make_models(args, want_gpu=False, want_oracle=True)
-    S, T = args.seqs_per_gpu, args.frames
-    feats = synthetic.make_features(S, T, seed=1234)
+    S_local, T = args.seqs_per_gpu, args.frames
+    S_total = S_local * world
+    block = min(64, S_total)
+    feats = synthetic.make_features(block, T, seed=1234)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     for _ in range(min(args.warmup, 1)):
-        oracle(feats[: max(1, S // 8)])
-    steps = max(1, min(args.steps, 20))                  # each step is a full 64x16 pass (~1 s of CPU work)
+        oracle(feats[: max(1, block // 8)])
+    steps = max(1, min(args.steps, 20 if world == 1 else 5))
+    n_blocks = (S_total + block - 1) // block
     times = []
     t_all = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        oracle(feats)
+        for _b in range(n_blocks):
+            oracle(feats)
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_all > 150:
             break
     ms = 1e3 * sum(times) / len(times)
-    value = S * T / (ms / 1e3)
+    value = n_blocks * block * T / (ms / 1e3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} full passes of {S}x{T} frames, torch {torch.__version__} CPU FP32, "
-                                   f"{cores} threads"},
+                         "sample": f"{len(times)} full passes of {S_total}x{T} frames in {n_blocks} block(s) of {block} sequences, "
+                                   f"torch {torch.__version__} CPU FP32, {cores} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, world, gather=None, chunks=None):
     jo = getattr(args, "joints_only", False)
-    return {"workload": (f"BASELINE configs[4] (joints-only): {args.seqs_per_gpu} sequences x {args.frames} frames per GPU, "
-                         "GRU(2048) + 3-iter HMR regressor + SMPL LBS, Kinect-25 output, no mesh write-back" if jo else
-                         f"BASELINE configs[1]: {args.seqs_per_gpu} sequences x {args.frames} frames per GPU, "
-                         "GRU(2048) + 3-iter HMR regressor + SMPL LBS, full 6890-vertex mesh + Kinect-25 output"),
-            "seqs_per_gpu": args.seqs_per_gpu, "frames_per_seq": args.frames,
-            "global_frames_per_step": args.seqs_per_gpu * args.frames * world, "smpl_weights": args.variant,
-            "sharding": f"sequences x{world}, no data-path collective" + ("" if args.gather == "none" else f", final all-gather: {args.gather}"),
-            "l2": "256 MiB L2 flush between timed steps (outside the event pairs); step working set ~0.5 GB > 126 MB L2",
+    S, T = args.seqs_per_gpu, args.frames
+    outs = "Kinect-25 output, no mesh write-back" if jo else "full 6890-vertex mesh + Kinect-25 output"
+    if world == 1:
+        wl = (f"BASELINE configs[{4 if jo else 1}]{' (joints-only)' if jo else ''}: {S} sequences x {T} frames on 1 B200, "
+              f"GRU(2048) + 3-iter HMR regressor + SMPL LBS, {outs}")
+        sharding = "one GPU"
+    else:
+        wl = (f"BASELINE configs[2]: {S * world} sequences x {T} frames, per-sequence sharded over {world} B200 ({S} per GPU), "
+              f"GRU(2048) + 3-iter HMR regressor + SMPL LBS, {outs}, final gather onto rank 0 inside the timed step")
+        sharding = (f"sequences x{world}, weights replicated, no data-path collective; final gather of "
+                    f"{'Kinect-25 joints' if jo else 'meshes + Kinect-25 joints'} onto rank 0: {gather or args.gather}"
+                    + (f", {chunks} chunk(s) per step" if chunks else ""))
+    return {"workload": wl, "seqs_per_gpu": S, "frames_per_seq": T, "global_frames_per_step": S * T * world,
+            "smpl_weights": args.variant, "sharding": sharding,
+            "l2": "256 MiB L2 flush between timed steps (outside the event pairs); step working set >= 0.5 GB > 126 MB L2",
             "regressor": "folded affine map (opt-in variant)" if getattr(args, "fold_regressor", False) else "3 iterations of fc1, fc2, decoders",
             "cuda_graph": not args.no_graph}
 
@@ -215,22 +248,270 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-# ------------------------------------------------------------------------------------------ GPU arm
-def run_b200(args, rank: int, local_rank: int, world: int):
-    import torch.distributed as dist
-    from gaitb200 import _lib, synthetic
-    from gaitb200.sharding import gather_sequences
+# ------------------------------------------------------------------------------------------ timing helpers
+class Timer:
+    """Device timing of repeated steps: per-step CUDA events on the launching stream, an L2 flush before every step
+    (outside the event pair), max over ranks of the summed step times."""
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (B200); the product has no CPU path. "
-                         "Use --impl reference for the CPU oracle arm.")
+    def __init__(self, dev, world):
+        import torch.distributed as dist
+        self.dev, self.world, self.dist = dev, world, dist
+        self.flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def flush_l2(self):
+        self.flush_buf.fill_(1.0)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return float(x)
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run(self, step_fn, steps, warmup):
+        """-> (ms per step [max over ranks of the mean], per-step ms list of this rank, wall seconds)"""
+        for _ in range(warmup):
+            self.flush_l2(); step_fn()
+        self.barrier()
+        evs = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            evs.append((a, b))
+        self.barrier()
+        wall = time.perf_counter() - t0
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return self.max_over_ranks(sum(ms)) / steps, ms, wall
+
+
+def measure_d2h_ceiling(timer, nbytes, repeats=6):
+    """What the box gives N ranks that copy `nbytes` device->pinned host at the same time with no kernel running: the
+    ceiling of the end-to-end number (GB/s per rank, max-over-ranks time)."""
+    dev_buf = torch.empty(nbytes // 4, device=timer.dev, dtype=torch.float32)
+    host = torch.empty(nbytes // 4).pin_memory()
+    host.copy_(dev_buf, non_blocking=True)
+    timer.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(repeats):
+        host.copy_(dev_buf, non_blocking=True)
+    b.record()
+    timer.barrier()
+    ms = timer.max_over_ranks(a.elapsed_time(b)) / repeats
+    del dev_buf, host
+    return nbytes / (ms * 1e-3) / 1e9
+
+
+def run_e2e(head, timer, args, feats_host, S, T, world):
+    """End to end through the public API: pinned host features -> H2D -> step -> D2H of every output (each rank its shard)."""
+    F = S * T
+    host_outs = [head.alloc_host_outputs() for _ in range(args.slots)]
+    feats_hosts = [feats_host, feats_host.clone().pin_memory()]
+    h2d = feats_host.numel() * 4
+    d2h = sum(v.numel() * 4 for v in host_outs[0].values())
+    e2e_steps = max(12, min(24, args.steps))
+    ins = [feats_hosts[i % 2] for i in range(e2e_steps)]
+    hos = [host_outs[i % args.slots] for i in range(e2e_steps)]
+    head.run_host_batches(ins[:4], hos[:4])                    # warm-up
+    timer.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    head.run_host_batches(ins, hos)
+    b.record()
+    timer.barrier()
+    e2e_ms = timer.max_over_ranks(a.elapsed_time(b)) / e2e_steps
+    ck = "kinect25" if not head.write_mesh else "verts"
+    last = (e2e_steps - 1) % args.slots
+    check = float((host_outs[last][ck] - head.outputs(last)[ck].cpu()).abs().max())
+    ceiling = measure_d2h_ceiling(timer, d2h)
+    d2h_gbs = d2h / (e2e_ms * 1e-3) / 1e9
+    del host_outs
+    return {"value": F * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": e2e_ms, "steps": e2e_steps, "d2h_gbs": d2h_gbs, "d2h_ceiling_gbs": ceiling,
+            "frac_of_d2h_ceiling": d2h_gbs / ceiling if ceiling else None,
+            "host_vs_device_max_abs_diff": check,
+            "note": "GaitHead.run_host_batches: copy-in / kernels / copy-out of consecutive batches overlap on 3 streams; D2H = one "
+                    "transfer of the packed output buffer [mesh | small outputs] per rank (h2d/d2h bytes are per rank); "
+                    "d2h_ceiling_gbs = the same D2H alone, all ranks at once, no kernels (per rank)"}
+
+
+def lbs_roofline(head, args, F, peaks, stages):
+    lbs_ms = head.time_stage_back_to_back("lbs", launches=8, repeats=5) if len(head._slots) >= 2 else stages["lbs"]["ms"]
+    jo = not head.write_mesh
+    lbs_bytes = F * (LBS_BYTES_PER_FRAME - (6890 * 3 * 4 - 21 * 12 if jo else 0)) + LBS_BYTES_ONCE
+    lbs_gbs = lbs_bytes / (lbs_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "lbs_traffic.json"          # dram bytes per launch from the committed ncu --set full capture
+    if tp.exists():
+        td = json.loads(tp.read_text())
+        if int(td.get("frames", -1)) == F and not jo:
+            traffic, traffic_src = td["dram_read_bytes"] + td["dram_write_bytes"], td.get("source")
+    return {"kernel": "smpl_lbs_tc_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peaks["source"], "frames_per_launch": F, "algorithmic_bytes_per_launch": lbs_bytes, "kernel_ms": lbs_ms,
+            "timing": ("8 consecutive launches between one CUDA-event pair on the launching stream, two alternating "
+                       "buffer sets (> 126 MB L2), best of 5") if len(head._slots) >= 2 else
+                      "one launch per CUDA-event pair after an L2 flush (one buffer slot)",
+            "kernel_ms_single_launch_event_pair": stages["lbs"]["ms"],
+            "frac_single_launch_event_pair": lbs_bytes / (stages["lbs"]["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+
+def stage_table(stages, F, peaks):
+    rep = {}
+    for name, s in stages.items():
+        e = {"ms": round(s["ms"], 5), "launches": s["launches"]}
+        if name in FLOPS_PER_FRAME:
+            tf = FLOPS_PER_FRAME[name] * F / (s["ms"] * 1e-3) / 1e12
+            e.update({"bound": "tensor", "achieved_tflops_fp32_equiv": round(tf, 3),
+                      "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 5),
+                      "frac_of_split_tf32_ceiling": round(tf / (peaks["bf16_tflops"] / 6), 4)})
+        rep[name] = e
+    return rep
+
+
+# ------------------------------------------------------------------------------------------ N = 1 sub-records
+def extra_configs(args, timer, peaks, feats_seed):
+    """The other BASELINE configurations on this one GPU (each a small device-timed record)."""
+    from gaitb200 import synthetic
+    out = {}
+    steps, warm = max(5, min(args.steps, 20)), max(3, min(args.warmup, 5))
+
+    def timed(head, S, T, steps=steps, capture=True):
+        (head.capture if capture else head.plan)(S, T, slots=1)
+        head.input.copy_(synthetic.make_features(S, T, seed=feats_seed))
+        ms, per, _ = timer.run(head.step, steps, warm)
+        return ms
+
+    # ---- c3_n1: all 1024 sequences of configs[2] on ONE GPU (the strong-scaling denominator of the N>1 lines)
+    a3 = copy.copy(args); a3.joints_only = False; a3.fold_regressor = False
+    head, _ = make_models(a3, want_gpu=True, want_oracle=False)
+    S3 = C3_SEQS
+    ms = timed(head, S3, args.frames, steps=max(5, steps // 2))
+    st = head.profile_stages(iters=3, flush=timer.flush_l2)
+    F3 = S3 * args.frames
+    lbs_b = F3 * LBS_BYTES_PER_FRAME + LBS_BYTES_ONCE
+    out["c3_n1"] = {"workload": f"BASELINE configs[2] on one GPU: {S3} sequences x {args.frames} frames, full mesh, no gather",
+                    "value": F3 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                    "stages_ms": {k: round(v["ms"], 4) for k, v in st.items()},
+                    "lbs_gbs": lbs_b / (st["lbs"]["ms"] * 1e-3) / 1e9, "lbs_frac": lbs_b / (st["lbs"]["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    # LBS rate at the per-GPU shard sizes of configs[2] (2048 / 4096 / 8192 / 16384 frames per launch)
+    sweep = {}
+    for S in (128, 256, 512):
+        head.plan(S, args.frames, slots=1)
+        head.input.copy_(synthetic.make_features(S, args.frames, seed=feats_seed))
+        s2 = head.profile_stages(iters=5, flush=timer.flush_l2)
+        Fs = S * args.frames
+        b = Fs * LBS_BYTES_PER_FRAME + LBS_BYTES_ONCE
+        sweep[str(Fs)] = {"lbs_ms": round(s2["lbs"]["ms"], 5), "lbs_gbs": round(b / (s2["lbs"]["ms"] * 1e-3) / 1e9, 1),
+                          "lbs_frac": round(b / (s2["lbs"]["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                          "gru_ms": round(s2["gru"]["ms"], 4), "step_ms_sum_of_stages": round(sum(v["ms"] for v in s2.values()), 4)}
+    sweep[str(F3)] = {"lbs_ms": round(st["lbs"]["ms"], 5), "lbs_gbs": round(out["c3_n1"]["lbs_gbs"], 1), "lbs_frac": round(out["c3_n1"]["lbs_frac"], 4),
+                      "gru_ms": round(st["gru"]["ms"], 4), "step_ms_sum_of_stages": round(sum(v["ms"] for v in st.values()), 4)}
+    out["c3_shard_sizes"] = {"note": "per-stage event timing (one launch per event pair, L2 flushed) at the per-GPU frame counts of configs[2]",
+                             "frames_per_launch": sweep}
+    del head
+    torch.cuda.empty_cache()
+
+    # ---- c4: one long clip, sequence-length sweep (S = 1): the GRU recurrence is T dependent steps
+    head, _ = make_models(a3, want_gpu=True, want_oracle=False)
+    c4 = {}
+    for T in (16, 64, 256, 450, 900):
+        ms = timed(head, 1, T, steps=max(5, steps // 2))
+        s4 = head.profile_stages(iters=3, flush=timer.flush_l2)
+        c4[str(T)] = {"value": T / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "gru_ms": round(s4["gru"]["ms"], 4),
+                      "gru_us_per_recurrence_step": round(1e3 * s4["gru"]["ms"] / T, 3),
+                      "other_stages_ms": round(sum(v["ms"] for k, v in s4.items() if k != "gru"), 4)}
+    out["c4"] = {"workload": "BASELINE configs[3]: one long gait clip (S = 1), T = 16..900 frames, full mesh (demo.py:149,415 chunks at 450)",
+                 "bound": "latency: T dependent recurrence steps; per step the GRU reads W_hh (50 MB) once",
+                 "by_frames": c4}
+    del head
+    torch.cuda.empty_cache()
+
+    # ---- c5: joints-only (no mesh write-back), same 64 x 16 batch
+    a5 = copy.copy(a3); a5.joints_only = True
+    head, _ = make_models(a5, want_gpu=True, want_oracle=False)
+    ms = timed(head, 64, args.frames)
+    s5 = head.profile_stages(iters=5, flush=timer.flush_l2)
+    out["c5"] = {"workload": "BASELINE configs[4] on one GPU: 64 sequences x 16 frames, Kinect-25 joints only (mesh never written to HBM)",
+                 "value": 64 * args.frames / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                 "stages_ms": {k: round(v["ms"], 4) for k, v in s5.items()},
+                 "bound": "not HBM-bound (2 020 B in, 300 B out per frame): tensor/latency-bound like the rest of the step"}
+    del head
+    torch.cuda.empty_cache()
+
+    # ---- c1: 1 sequence x 16 frames, batch 1: CPU oracle (BASELINE configs[0]) and the GPU path at the same shape
+    head, oracle = make_models(a3, want_gpu=True, want_oracle=not args.no_cpu_baseline)
+    ms = timed(head, 1, 16)
+    c1 = {"workload": "BASELINE configs[0]: 1 sequence x 16 frames, batch 1, FP32",
+          "gpu": {"value": 16 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms}}
+    if oracle is not None:
+        v, runs, sec = time_oracle(oracle, synthetic.make_features(1, 16, seed=feats_seed), 3.0, min_runs=3, max_runs=20)
+        c1["cpu"] = {"value": v, "unit": UNIT, "ms_per_step": sec * 1e3, "cores": os.cpu_count() or 1, "kind": "port",
+                     "sample": f"best of {runs} passes of 1x16 frames, oracle/ torch {torch.__version__} CPU FP32"}
+    out["c1"] = c1
+    del head
+    torch.cuda.empty_cache()
+    return out
+
+
+def jreg_stage(args, timer, peaks, F):
+    """The standalone joint-regressor kernel (pare.py:70-76 / spin.py:279-282: J_regressor (17,6890) . verts) as an HBM stream."""
+    from gaitb200 import _lib as L, synthetic
+    lib = L.load()
+    dev = timer.dev
+    V, rows = 6890, 17
+    jr = torch.as_tensor(synthetic.make_smpl_data(seed=0, variant=args.variant)["J_regressor_h36m"], device=dev).contiguous()
+    bufs = [torch.randn(F, V, 3, device=dev) for _ in range(2)]          # 2 x 84.7 MB: alternate so no launch finds its input in L2
+    out = torch.empty(F, rows, 3, device=dev)
+    st = L.stream_ptr
+    packed = torch.empty(lib.gait_joint_regress_pack_bytes(V, rows) // 4, device=dev)
+    L.call("gait_joint_regress_pack", L.ptr(jr), L.ptr(packed), V, rows, st())
+    run = lambda b: L.call("gait_joint_regress_packed", L.ptr(b), L.ptr(packed), L.ptr(out), F, V, rows, st())
+    for b in bufs:
+        run(b)
+    torch.cuda.synchronize()
+    ref = torch.einsum("jv,fvc->fjc", jr.double(), bufs[1].double()).float()
+    err = float((out - ref).abs().max())
+    best = float("inf")
+    n0 = L.launch_count()
+    for _ in range(5):
+        timer.flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(8):
+            run(bufs[i % 2])
+        b.record(); b.synchronize()
+        best = min(best, a.elapsed_time(b) / 8)
+    launches = (L.launch_count() - n0) // 40
+    nbytes = F * JREG_BYTES_PER_FRAME(rows) + JREG_BYTES_ONCE(rows)
+    gbs = nbytes / (best * 1e-3) / 1e9
+    return {"kernel": "joint_regress_stream_kernel<17>", "rows": rows, "frames": F, "ms": best, "launches": launches, "bound": "hbm", "achieved_gbs": gbs,
+            "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": nbytes, "max_abs_err_vs_fp64": err,
+            "timing": "8 consecutive launches between one CUDA-event pair, two alternating 84.7 MB inputs, best of 5",
+            "note": "J_regressor (17,6890) . verts (pare.py:70-76, spin.py:279-282): lane = frame, weights staged by TMA bulk copies, "
+                    "vertices streamed by cp.async, 8-CTA clusters + DSMEM reduction"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm, N = 1
+def run_single(args, local_rank: int):
+    from gaitb200 import _lib, synthetic
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     S, T = args.seqs_per_gpu, args.frames
     F = S * T
     peaks = load_peaks()
+    timer = Timer(dev, 1)
     head, _ = make_models(args, want_gpu=True, want_oracle=False)
-    feats_host = synthetic.make_features(S, T, seed=1234 + rank).pin_memory()
+    feats_host = synthetic.make_features(S, T, seed=1234).pin_memory()
 
     if args.no_graph:
         head.plan(S, T, slots=args.slots)
@@ -243,130 +524,35 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     head.input.copy_(feats_host, non_blocking=True)
     torch.cuda.synchronize()
 
-    flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
-
-    def flush_l2():
-        flush_buf.fill_(1.0)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def gather():
-        if world > 1 and args.gather != "none":
-            o = head.outputs()
-            gather_sequences(o["kinect25"], S * world)
-            if args.gather == "mesh":
-                gather_sequences(o["verts"], S * world)
-
     # ---- device-resident throughput: inputs already in HBM, per-step CUDA events, L2 flushed between steps
-    for _ in range(args.warmup):
-        flush_l2(); head.step(); gather()
-    barrier()
-    evs = []
     with ClockSampler(local_rank) as clocks:
-        t_wall0 = time.perf_counter()
-        for _ in range(args.steps):
-            flush_l2()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            head.step()
-            gather()
-            b.record()
-            evs.append((a, b))
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms_local = sum(step_ms)
-    t = torch.tensor([total_ms_local], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = F * world * args.steps / (total_ms / 1e3)
+        ms_per_step, step_ms, t_wall = timer.run(head.step, args.steps, args.warmup)
+    value = F / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API: pinned host features -> H2D -> step -> D2H of every output.
-    # GaitHead.run_host_batches overlaps copy-in / kernels / copy-out of consecutive batches (two buffer slots).
-    outs = head.outputs()
-    host_outs = [head.alloc_host_outputs() for _ in range(args.slots)]
-    feats_hosts = [feats_host, feats_host.clone().pin_memory()]
-    h2d = feats_host.numel() * 4
-    d2h = sum(v.numel() * 4 for v in host_outs[0].values())
-    e2e_steps = max(24, args.steps // 2)
-    ins = [feats_hosts[i % 2] for i in range(e2e_steps)]
-    hos = [host_outs[i % args.slots] for i in range(e2e_steps)]
-    head.run_host_batches(ins[:4], hos[:4])                    # warm-up
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    head.run_host_batches(ins, hos)
-    b.record()
-    barrier()
-    te = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item()) / e2e_steps
-    e2e_value = F * world / (e2e_ms / 1e3)
-    ck = "kinect25" if args.joints_only else "verts"
-    e2e_check = float((host_outs[(e2e_steps - 1) % args.slots][ck] - head.outputs((e2e_steps - 1) % args.slots)[ck].cpu()).abs().max())
+    e2e = run_e2e(head, timer, args, feats_host, S, T, 1)
 
-    if rank != 0:
-        return
     # ---- per-stage timings (eager launches, L2 flushed before each) and rooflines
-    stages = head.profile_stages(iters=10, flush=flush_l2)
-    # dominant HBM kernel: average launch duration over 8 consecutive launches between one event pair, alternating
-    # two buffer sets (2 x 170 MB > L2); the single-launch figure (own event pair after an L2 flush) is kept beside it
-    lbs_ms = head.time_stage_back_to_back("lbs", launches=8, repeats=5) if args.slots >= 2 else stages["lbs"]["ms"]
-    lbs_bytes = F * (LBS_BYTES_PER_FRAME - (6890 * 3 * 4 - 21 * 12 if args.joints_only else 0)) + LBS_BYTES_ONCE
-    lbs_gbs = lbs_bytes / (lbs_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    tp = ROOT / "profiles" / "lbs_traffic.json"          # dram bytes per launch from the committed ncu --set full capture
-    if tp.exists():
-        td = json.loads(tp.read_text())
-        if int(td.get("frames", -1)) == F and not args.joints_only:
-            traffic, traffic_src = td["dram_read_bytes"] + td["dram_write_bytes"], td.get("source")
-    roofline = {"kernel": "smpl_lbs_tc_kernel", "bound": "hbm", "achieved": lbs_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peaks["source"], "algorithmic_bytes_per_launch": lbs_bytes, "kernel_ms": lbs_ms,
-                "timing": ("8 consecutive launches between one CUDA-event pair on the launching stream, two alternating "
-                           "buffer sets (340 MB > 126 MB L2), best of 5") if args.slots >= 2 else
-                          "one launch per CUDA-event pair after an L2 flush (--slots 1)",
-                "kernel_ms_single_launch_event_pair": stages["lbs"]["ms"],
-                "frac_single_launch_event_pair": lbs_bytes / (stages["lbs"]["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-    stage_report = {}
-    for name, s in stages.items():
-        e = {"ms": round(s["ms"], 5), "launches": s["launches"]}
-        if name in FLOPS_PER_FRAME:
-            tf = FLOPS_PER_FRAME[name] * F / (s["ms"] * 1e-3) / 1e12
-            e.update({"bound": "tensor", "achieved_tflops_fp32_equiv": round(tf, 3),
-                      "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 5)})
-        stage_report[name] = e
-    lbs_gbs1 = lbs_bytes / (stages["lbs"]["ms"] * 1e-3) / 1e9
+    stages = head.profile_stages(iters=10, flush=timer.flush_l2)
+    roofline = lbs_roofline(head, args, F, peaks, stages)
+    stage_report = stage_table(stages, F, peaks)
+    lbs_gbs1 = roofline["algorithmic_bytes_per_launch"] / (stages["lbs"]["ms"] * 1e-3) / 1e9
     stage_report["lbs"].update({"bound": "hbm", "achieved_gbs": round(lbs_gbs1, 1), "frac": round(lbs_gbs1 / peaks["hbm_gbs"], 4)})
     stage_report["lbs"]["note"] = ("tcgen05 split-TF32 W.A + SIMT apply; J_regressor_extra thorax row fused as per-tile partials "
                                    "(no separate joint-regression pass over the vertices)")
+    jreg = jreg_stage(args, timer, peaks, F)
+    if jreg is not None:
+        stage_report["jreg"] = jreg
 
     # ---- opt-in variant reported beside the headline: regressor loop folded into one affine map (same outputs)
     folded = None
-    if world == 1 and not args.fold_regressor and not args.no_graph:
-        import copy
+    ck = "kinect25" if args.joints_only else "verts"
+    if not args.fold_regressor and not args.no_graph:
         fargs = copy.copy(args)
         fargs.fold_regressor = True
         fhead, _ = make_models(fargs, want_gpu=True, want_oracle=False)
         fhead.capture(S, T, slots=1)
         fhead.input.copy_(feats_host, non_blocking=True)
-        for _ in range(args.warmup):
-            flush_l2(); fhead.step()
-        torch.cuda.synchronize()
-        fev = []
-        for _ in range(args.steps):
-            flush_l2()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fhead.step(); b.record()
-            fev.append((a, b))
-        torch.cuda.synchronize()
-        fms = sum(a.elapsed_time(b) for a, b in fev) / args.steps
+        fms, _, _ = timer.run(fhead.step, args.steps, args.warmup)
         fdiff = {k: float((fhead.outputs()[k] - head.outputs()[k]).abs().max()) for k in ("rotmat", ck)}
         folded = {"value": F / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "launches_per_step": fhead.launches_per_step,
                   "max_abs_diff_vs_loop": fdiff,
@@ -375,32 +561,168 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         del fhead
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:
         _, oracle = make_models(args, want_gpu=False, want_oracle=True)
         cores = os.cpu_count() or 1
         v, runs, sec = time_oracle(oracle, feats_host.clone(), args.cpu_baseline_seconds)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"best of {runs} full passes of {S}x{T} frames ({sec:.3f} s each), oracle/ torch "
                                   f"{torch.__version__} CPU FP32, {cores} threads"}
+    del head
+    torch.cuda.empty_cache()
+    configs = None if (args.no_extra_configs or args.joints_only or args.fold_regressor or args.no_graph) \
+        else extra_configs(args, timer, peaks, 4321)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, world),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "scaling_note": "N=1 runs BASELINE configs[1] (64 sequences); the N>1 lines run configs[2] (1024 sequences sharded, gather "
+                        "inside the step): their one-GPU denominator is configs.c3_n1.value of this line",
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "steps": e2e_steps, "d2h_gbs": d2h / (e2e_ms * 1e-3) / 1e9,
-                "host_vs_device_max_abs_diff": e2e_check,
-                "note": "GaitHead.run_host_batches: copy-in / kernels / copy-out of consecutive batches overlap on 3 streams; "
-                        "D2H = one transfer of the packed output buffer [mesh | small outputs]; PCIe D2H measured ceiling on this box ~57 GB/s"},
+        "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": roofline,
         "stages": stage_report,
         "folded_regressor_variant": folded,
         "cpu_baseline": cpu_baseline,
+        "configs": configs,
         "whole_step_hbm_frac": (F * (IN_BYTES_PER_FRAME + OUT_BYTES_PER_FRAME - (6890 * 12 if args.joints_only else 0))
                                 / (ms_per_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
+        "wall_s_timed_region": t_wall,
+        "step_ms_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
+        "library": str(_lib.LIB_PATH.relative_to(ROOT)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm, N > 1
+def run_sharded(args, rank: int, local_rank: int, world: int):
+    import torch.distributed as dist
+    from gaitb200 import _lib, synthetic
+    from gaitb200.sharding import PeerUnavailable, RootGather
+
+    dev = torch.device("cuda", local_rank)
+    S, T = args.seqs_per_gpu, args.frames
+    S_total = S * world
+    F = S * T
+    peaks = load_peaks()
+    timer = Timer(dev, world)
+    feats_host = synthetic.make_features(S, T, seed=1234 + rank).pin_memory()
+    head, _ = make_models(args, want_gpu=True, want_oracle=False)
+    short = max(5, min(10, args.steps))
+
+    def build(mode, chunks, h=head):
+        try:
+            rg = RootGather(h, S_total, T, mode=mode, chunks=chunks, use_graphs=not args.no_graph)
+        except PeerUnavailable as e:
+            return None, repr(e)
+        rg.load_features(feats_host)
+        torch.cuda.synchronize()
+        return rg, None
+
+    # ---- candidates for the final gather; every one is timed (short), the fastest is the headline
+    if args.gather == "auto":
+        cands = [("peer-store", args.chunks or 1), ("peer-copy", args.chunks or 2), ("nccl", args.chunks or 1)]
+    elif args.gather == "none":
+        cands = []
+    else:
+        cands = [(args.gather, args.chunks or (2 if args.gather == "peer-copy" else 1))]
+    variants, best = {}, None
+    for mode, chunks in cands:
+        rg, err = build(mode, chunks)
+        key = f"{mode}/chunks={chunks}"
+        if rg is None:
+            variants[key] = {"unavailable": err}
+            continue
+        ms, _, _ = timer.run(rg.run, short, 3)
+        variants[key] = {"ms_per_step": ms, "value": S_total * T / (ms * 1e-3), "steps": short}
+        if best is None or ms < best[2]:
+            best = (mode, chunks, ms)
+        rg.close()
+        del rg
+        torch.cuda.empty_cache()
+
+    # ---- compute only (no gather), same shard: what the exchange costs
+    head.capture(S, T, slots=1) if not args.no_graph else head.plan(S, T, slots=1)
+    head.input.copy_(feats_host, non_blocking=True)
+    ms_nogather, _, _ = timer.run(head.step, short, 3)
+    launches_per_chunk = head.launches_per_step if not args.no_graph else None
+
+    # ---- headline: the chosen gather inside the timed step
+    if best is not None:
+        mode, chunks, _ = best
+        rg, err = build(mode, chunks)
+        step_fn, launches_per_step = rg.run, (rg.launches_per_step or 0)
+        ingest = rg.root_ingest_bytes
+    else:
+        mode, chunks, rg = "none", 1, None
+        step_fn, launches_per_step, ingest = head.step, (launches_per_chunk or 0), 0
+    with ClockSampler(local_rank) as clocks:
+        ms_per_step, step_ms, t_wall = timer.run(step_fn, args.steps, args.warmup)
+    value = S_total * T / (ms_per_step * 1e-3)
+    gather_check = None
+    if rg is not None:
+        # the gathered block of the LAST rank on the root equals what that rank computed (one small all-to-root check)
+        loc = rg.local_outputs()["kinect25"]
+        last = torch.empty_like(loc)
+        if rank == world - 1:
+            dist.send(loc.contiguous(), 0)
+        if rank == 0:
+            dist.recv(last, world - 1)
+            gather_check = float((rg.gathered()["kinect25"][S_total - S:] - last).abs().max())
+        rg.close()
+        del rg
+        torch.cuda.empty_cache()
+
+    # ---- c5 at N GPUs: joints-only shard + gather of the Kinect-25 joints
+    c5 = None
+    if not args.joints_only and args.gather != "none":
+        a5 = copy.copy(args); a5.joints_only = True
+        h5, _ = make_models(a5, want_gpu=True, want_oracle=False)
+        rg5, err = build(best[0] if best and best[0] != "peer-store" else "peer-copy", 1, h5)
+        if rg5 is None:
+            rg5, err = build("nccl", 1, h5)
+        ms5, _, _ = timer.run(rg5.run, short, 3)
+        c5 = {"workload": f"BASELINE configs[4]: joints-only (no mesh write-back) at {world} B200, {S_total} sequences, Kinect-25 gather onto rank 0 ({rg5.mode})",
+              "value": S_total * T / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "root_ingest_bytes_per_step": rg5.root_ingest_bytes,
+              "full_mesh_value": value, "speedup_vs_full_mesh": ms_per_step / ms5}
+        rg5.close()
+        del rg5, h5
+        torch.cuda.empty_cache()
+
+    # ---- end to end (each rank: pinned host features -> H2D -> step -> D2H of its shard's outputs), stages, roofline
+    head.capture(S, T, slots=args.slots) if not args.no_graph else head.plan(S, T, slots=args.slots)
+    head.input.copy_(feats_host, non_blocking=True)
+    e2e = run_e2e(head, timer, args, feats_host, S, T, world)
+    if rank != 0:
+        return
+    stages = head.profile_stages(iters=5, flush=timer.flush_l2)
+    roofline = lbs_roofline(head, args, F, peaks, stages)
+    stage_report = stage_table(stages, F, peaks)
+
+    link_gbs = ingest / (max(ms_per_step - ms_nogather, 1e-6) * 1e-3) / 1e9 if ingest else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, world, gather=mode, chunks=chunks),
+        "clocks": clocks.summary(),
+        "gather": {"mode": mode, "chunks": chunks, "root_ingest_bytes_per_step": ingest,
+                   "ms_per_step_without_gather": ms_nogather, "value_without_gather": S_total * T / (ms_nogather * 1e-3),
+                   "exposed_gather_ms": ms_per_step - ms_nogather,
+                   "root_ingest_gbs_if_not_overlapped": link_gbs,
+                   "nvlink5_ingest_floor_ms": ingest / 900e9 * 1e3 if ingest else 0.0,
+                   "limiter": "rank 0 receives (N-1)/N of all meshes through its own NVLink 5 port (900 GB/s per direction): "
+                              "the floor above is that transfer alone; chunks > 1 overlap it with the next chunk's compute",
+                   "variants": variants, "root_vs_last_rank_kinect25_max_abs_diff": gather_check},
+        "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "roofline": roofline,
+        "stages": stage_report,
+        "configs": {"c5": c5} if c5 else None,
+        "cpu_baseline": None,
         "wall_s_timed_region": t_wall,
         "step_ms_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
         "library": str(_lib.LIB_PATH.relative_to(ROOT)),
@@ -414,18 +736,22 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
-    if world > 1:
-        from gaitb200.sharding import init_from_env
-        init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); the product has no CPU path. "
+                         "Use --impl reference for the CPU oracle arm.")
+    if world == 1:
+        run_single(args, local_rank)
+        return
+    from gaitb200.sharding import init_from_env
+    init_from_env("nccl")
     try:
-        run_b200(args, rank, local_rank, world)
+        run_sharded(args, rank, local_rank, world)
     finally:
-        if world > 1:
-            import torch.distributed as dist
-            if dist.is_initialized():
-                dist.destroy_process_group()
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -181,8 +181,9 @@ int gait_smpl_lbs(const float* v_posed, int64_t ldv, const float* A, const float
  *   Aop    = the pose-chain kernel's tensor operand output
  *   v_posed rows padded: ldv >= 384*ceil(V/128), ldv % 4 == 0 (rows are bulk-copied 1536 B at a time)
  *   jx (V) optional: one joint-regressor row (the MPII thorax row of J_regressor_extra); its dot
- *   product with the skinned vertices is emitted as per-vertex-tile partial sums
- *   jx_partial (ceil(V/128), F, 3), summed by gait_joints_assemble (extra_parts = ceil(V/128)). */
+ *   product with the skinned vertices is emitted as partial sums over 32-vertex slices,
+ *   jx_partial (gait_smpl_lbs_jx_parts(V) = 4*ceil(V/128), F, 3), summed by gait_joints_assemble (extra_parts = that). */
+int64_t gait_smpl_lbs_jx_parts(int64_t V);
 size_t gait_smpl_lbs_pack_bytes(int64_t V);
 int gait_smpl_lbs_pack(const float* lbs_weights, float* packed, int64_t V, gait_stream_t stream);
 size_t gait_smpl_lbs_aop_bytes(int64_t F);
@@ -195,10 +196,24 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
 int gait_smpl_lbs_tc_joints(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
                             float* jx_partial, const int32_t* lm_idx, int n_lm, float* lm_out, int64_t F, int64_t V,
                             gait_stream_t stream);
+/* General form: verts (F,V,3) and/or lm_out (F,n_lm,3) (either may be NULL, not both).  With both, the mesh goes to `verts`
+ * - which may be a PEER address (gait_peer_open): the kernel's coalesced stores then are the final gather of a
+ * sequence-sharded run - while the landmark vertices the joint sets read stay in local memory. */
+int gait_smpl_lbs_tc_ex(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                        float* verts, float* jx_partial, const int32_t* lm_idx, int n_lm, float* lm_out, int64_t F,
+                        int64_t V, gait_stream_t stream);
 /* vertices2joints (smplx lbs; lib/models/smpl.py:113, pare.py:70-76, spin.py:279-282):
  * out (F,Rj,3) = Jreg (Rj,V) . verts (F,V,3). */
 int gait_joint_regress(const float* verts, const float* Jreg, float* out, int64_t F, int64_t V, int Rj,
                        gait_stream_t stream);
+/* The same regression as ONE streaming pass over the mesh (lane = frame, all Rj rows per pass, 8-CTA clusters splitting the
+ * vertex range, partial sums combined through distributed shared memory; jreg.cu).  The regressor is packed once
+ * (gait_joint_regress_pack -> gait_joint_regress_pack_bytes(V,Rj) bytes, 16-byte aligned: [row block][4-vertex group][row][4],
+ * zero padded) so that every pipeline stage stages its weights with one TMA bulk copy.  verts (F,V,3) contiguous, V even. */
+size_t gait_joint_regress_pack_bytes(int64_t V, int Rj);
+int gait_joint_regress_pack(const float* Jreg, float* packed, int64_t V, int Rj, gait_stream_t stream);
+int gait_joint_regress_packed(const float* verts, const float* packed, float* out, int64_t F, int64_t V, int Rj,
+                              gait_stream_t stream);
 /* Joint assembly (smplx VertexJointSelector + smpl.py:114-121) with optional projection
  * (smpl.py:176-186 / geometry.py:412-425) and Kinect-25 gather (kp_utils.py:26-36).
  * Virtual joint v: v<24 -> J_posed; 24<=v<24+n_landmarks -> verts[landmark[v-24]];
@@ -221,6 +236,22 @@ int gait_gather_joints(const float* src, int Js, const int32_t* idx, int Jd, flo
  * axis-angle from R (F,24,3,3) by the geometry.py:68-97 route. */
 int gait_pack_theta(const float* R, const float* cam, int64_t ldcam, const float* betas, int64_t ldb,
                     float* theta, int64_t F, gait_stream_t stream);
+
+/* ---- peer memory: the final gather of a sequence-sharded run ---------------- */
+/* The one exchange on the path is the gather of meshes / Kinect-25 joints onto one rank; it replaces the per-process
+ * device-to-host boundary batch_generation.py:316-323 / demo.py:183-188.  The root allocates the gathered buffer
+ * (gait_peer_alloc: the one place this library allocates, because a CUDA IPC handle maps a whole allocation), exports a
+ * 64-byte handle that the host side ships to the other processes (any transport), and they map it (gait_peer_open).
+ * Ranks then write their blocks either with gait_smpl_lbs_tc_ex(verts = mapped address) or with gait_peer_copy
+ * (asynchronous device-to-device copy on `stream`; dst/src may be local or mapped).  Completion is stream-ordered on the
+ * writer; the host side signals the root (a collective or event) before it reads. */
+#define GAIT_PEER_HANDLE_BYTES 64
+int gait_peer_alloc(void** ptr, size_t bytes);
+int gait_peer_free(void* ptr);
+int gait_peer_export(const void* ptr, unsigned char handle[GAIT_PEER_HANDLE_BYTES]);
+int gait_peer_open(const unsigned char handle[GAIT_PEER_HANDLE_BYTES], void** ptr);
+int gait_peer_close(void* ptr);
+int gait_peer_copy(void* dst, const void* src, size_t bytes, gait_stream_t stream);
 
 /* ---- post-processing next to the head ------------------------------ */
 /* One-Euro filter (lib/utils/one_euro_filter.py:5-46) over T frames of C channels, as lib/utils/smooth_pose.py:51-56,

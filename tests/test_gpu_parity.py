@@ -285,7 +285,7 @@ def test_lbs_kernels_vs_oracle(variant, F, lib_loaded):
     Tc = torch.matmul(W.unsqueeze(0).expand(F, -1, -1), Ac.view(F, 24, 16)).view(F, V, 4, 4)
     refc = torch.matmul(Tc, torch.cat([vp, torch.ones(F, V, 1)], 2).unsqueeze(-1))[:, :, :3, 0]
     jx = T(data["J_regressor_extra"][5]).cuda()
-    part = torch.empty(54, F, 3, device="cuda")
+    part = torch.empty(lib.gait_smpl_lbs_jx_parts(V), F, 3, device="cuda")
     out2 = torch.empty(F, V, 3, device="cuda")
     L.call("gait_smpl_lbs_tc", vpp.data_ptr(), ldv, aop.data_ptr(), wpack.data_ptr(), jx.data_ptr(), out2.data_ptr(),
            part.data_ptr(), F, V, st)
@@ -743,3 +743,41 @@ def test_heads_vs_reference_golden(golden, lib_loaded):
     assert maxerr(y, g["bm_y"]) <= 1e-5 and maxerr(p, g["bm_p"]) <= 1e-5 and maxerr(xc[:, :, ::7], g["bm_xc"]) <= 1e-6
     with pytest.raises(NotImplementedError):
         BidirectionalModel(seqlen=16, use_pareFeat=False)
+
+
+@pytest.mark.parametrize("F,Rj,variant", [(8, 17, "sparse"), (33, 17, "dense"), (70, 9, "sparse"), (64, 24, "dense"), (1000, 17, "sparse"),
+                                          (40, 49, "dense"), (9, 1, "sparse")])
+def test_joint_regress_stream_kernel(F, Rj, variant, lib_loaded):
+    """The streaming joint-regressor kernel (jreg.cu: lane = frame, TMA-staged packed weights, cluster/DSMEM reduction) against
+    an FP64 einsum and against the generic kernel, for the row counts the reference uses (17 H36M rows pare.py:70-76 /
+    spin.py:279-282, 9 extra rows smpl.py:113, 24 rest-joint rows) and ragged frame counts."""
+    L = lib_loaded
+    lib = L.load()
+    V = 6890
+    g = torch.Generator().manual_seed(F * 100 + Rj)
+    if variant == "dense":
+        Jr = torch.rand(Rj, V, generator=g) + 1e-3
+    else:
+        Jr = torch.zeros(Rj, V)
+        for r in range(Rj):
+            idx = torch.randperm(V, generator=g)[:40]
+            Jr[r, idx] = torch.rand(40, generator=g) + 0.05
+    Jr = (Jr / Jr.sum(1, keepdim=True)).cuda().contiguous()
+    verts = (torch.randn(F, V, 3, generator=g) * 0.5).cuda()
+    ref = torch.einsum("jv,fvc->fjc", Jr.double(), verts.double()).float()
+    st = L.stream_ptr()
+    packed = torch.full((lib.gait_joint_regress_pack_bytes(V, Rj) // 4,), float("nan"), device="cuda")
+    L.call("gait_joint_regress_pack", Jr.data_ptr(), packed.data_ptr(), V, Rj, st)
+    out = torch.full((F, Rj, 3), float("nan"), device="cuda")
+    L.call("gait_joint_regress_packed", verts.data_ptr(), packed.data_ptr(), out.data_ptr(), F, V, Rj, st)
+    assert maxerr(out, ref) <= 2e-6
+    old = torch.empty(F, Rj, 3, device="cuda")
+    L.call("gait_joint_regress", verts.data_ptr(), Jr.data_ptr(), old.data_ptr(), F, V, Rj, st)
+    assert maxerr(out, old) <= 2e-6
+    out2 = torch.empty_like(out)
+    L.call("gait_joint_regress_packed", verts.data_ptr(), packed.data_ptr(), out2.data_ptr(), F, V, Rj, st)
+    assert torch.equal(out, out2)                     # fixed summation order: bitwise repeatable
+    # the Python entry (packed-weight cache keyed on the tensor; re-packed after an in-place change)
+    assert torch.equal(L.joint_regress(verts, Jr), out)
+    Jr.mul_(2.0)
+    assert maxerr(L.joint_regress(verts, Jr), 2 * ref) <= 4e-6

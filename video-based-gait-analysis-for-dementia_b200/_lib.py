@@ -49,12 +49,23 @@ _SIGS = {
     "gait_smpl_pose_chain_rot6d": [P, I64, F32, P, I64, P, I64, P, P, P, P, P, P, P, P, P, I64, P],
     "gait_smpl_blend": [P, P, P, I64, I64, I64, P],
     "gait_smpl_lbs": [P, I64, P, P, P, I64, I64, P],
+    "gait_smpl_lbs_jx_parts": [I64],
     "gait_smpl_lbs_pack_bytes": [I64],
     "gait_smpl_lbs_pack": [P, P, I64, P],
     "gait_smpl_lbs_aop_bytes": [I64],
     "gait_smpl_lbs_tc": [P, I64, P, P, P, P, P, I64, I64, P],
     "gait_smpl_lbs_tc_joints": [P, I64, P, P, P, P, P, I32, P, I64, I64, P],
+    "gait_smpl_lbs_tc_ex": [P, I64, P, P, P, P, P, P, I32, P, I64, I64, P],
+    "gait_peer_alloc": [C.POINTER(P), SZ],
+    "gait_peer_free": [P],
+    "gait_peer_export": [P, C.c_char_p],
+    "gait_peer_open": [C.c_char_p, C.POINTER(P)],
+    "gait_peer_close": [P],
+    "gait_peer_copy": [P, P, SZ, P],
     "gait_joint_regress": [P, P, P, I64, I64, I32, P],
+    "gait_joint_regress_pack_bytes": [I64, I32],
+    "gait_joint_regress_pack": [P, P, I64, I32, P],
+    "gait_joint_regress_packed": [P, P, P, I64, I64, I32, P],
     "gait_joints_assemble": [P, P, I64, P, I32, P, I32, I32, I64, P, I32, P, P, I64, F32, F32, F32, P, P, I32, P, I64, P],
     "gait_gather_joints": [P, I32, P, I32, P, I64, P],
     "gait_one_euro_filter": [P, P, I64, I64, F64, F64, F64, P],
@@ -72,8 +83,10 @@ _RESTYPES = {
     "gait_gru_workspace_bytes": SZ,
     "gait_hmr_workspace_bytes": SZ,
     "gait_hmr_folded_workspace_bytes": SZ,
+    "gait_smpl_lbs_jx_parts": I64,
     "gait_smpl_lbs_pack_bytes": SZ,
     "gait_smpl_lbs_aop_bytes": SZ,
+    "gait_joint_regress_pack_bytes": SZ,
 }
 EXPORTS = tuple(_SIGS)
 
@@ -150,6 +163,32 @@ def prepare_weight(w: torch.Tensor) -> torch.Tensor:
 
 def release_weight(w: torch.Tensor):
     _drop_prepared(w.data_ptr())
+
+
+_packed_jreg = {}      # id(tensor) -> (weakref to the regressor tensor, its _version, data_ptr, packed tensor); at most 8 entries
+
+
+def joint_regress(verts: torch.Tensor, Jr: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out (F,Rj,3) = Jr (Rj,V) . verts (F,V,3)  (pare.py:70-76, spin.py:279-282, smpl.py:113).  Batches of >= 8 frames take the
+    streaming cluster kernel (jreg.cu) with the regressor packed once per tensor (re-packed when it was modified in place or
+    replaced); tiny batches (model preparation) take the generic kernel."""
+    import weakref
+    F, V, Rj = verts.shape[0], verts.shape[1], Jr.shape[0]
+    if out is None:
+        out = torch.empty(F, Rj, 3, device=verts.device, dtype=torch.float32)
+    if F < 8 or V % 2 or verts.data_ptr() % 8:
+        call("gait_joint_regress", ptr(verts), ptr(Jr), ptr(out), F, V, Rj, stream_ptr())
+        return out
+    key = id(Jr)
+    hit = _packed_jreg.get(key)
+    if hit is None or hit[0]() is not Jr or hit[1] != Jr._version or hit[2] != Jr.data_ptr():
+        packed = torch.empty(load().gait_joint_regress_pack_bytes(V, Rj) // 4, device=Jr.device, dtype=torch.float32)
+        call("gait_joint_regress_pack", ptr(Jr), ptr(packed), V, Rj, stream_ptr())
+        if len(_packed_jreg) >= 8:
+            _packed_jreg.pop(next(iter(_packed_jreg)))
+        _packed_jreg[key] = hit = (weakref.ref(Jr, lambda _r, k=key: _packed_jreg.pop(k, None)), Jr._version, Jr.data_ptr(), packed)
+    call("gait_joint_regress_packed", ptr(verts), ptr(hit[3]), ptr(out), F, V, Rj, stream_ptr())
+    return out
 
 
 def launch_count() -> int:

@@ -108,7 +108,12 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
     if (gru_path != 1 && linear_path() != 1) {
         // up to 192 sequences run as consecutive 64-sequence launches of the persistent kernel (beyond that the per-step
         // GEMMs, whose efficiency grows with the number of rows, win; measured with scripts/stage_sweep.py)
-        constexpr int64_t kChunk = 64, kMaxChunked = 192;
+        constexpr int64_t kChunk = 64;
+        static int64_t kMaxChunked = -1;              // GAITB200_GRU_MAXCHUNKED: A/B switch for the crossover (scripts/gru_s_sweep.py)
+        if (kMaxChunked < 0) {
+            const char* e = getenv("GAITB200_GRU_MAXCHUNKED");
+            kMaxChunked = e ? atoll(e) : 192;
+        }
         const int64_t S0 = std::min<int64_t>(S, kChunk);
         if (S <= kMaxChunked && gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S0, T, H)) {
             unsigned int* counter = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);

@@ -117,19 +117,38 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
 //                              (= vertices): tcgen05.ld T for 8 frames, apply to v_posed in smem, fused
 //                              regressor-row partial, coalesced stores, then release the stage
 // Loads run up to 3 items ahead and two epilogues are in flight, which hides the TMA/HBM/TMEM latencies.
-constexpr int NS = 6;                                    // shared-memory stages: ~180 KB of loads in flight per SM (HBM latency)
+// Two shared-memory rings, decoupled because their latencies differ by an order of magnitude: the transform blobs come
+// from L2 (2.4 MB per 1024 frames, re-read by all 54 vertex tiles) and are released as soon as the MMAs of the item have
+// retired; the v_posed rows come from HBM and their slot doubles as the output staging buffer, so it is held until the
+// consumer group has stored the skinned vertices.  With ONE ring of 6 combined stages only ~3 HBM loads were in flight per
+// SM (the other 3 slots being processed by the 3 consumer groups): the kernel sat at 4.0-4.7 TB/s with nothing saturated.
+#ifndef GAIT_LBS_NA
+#define GAIT_LBS_NA 3
+#endif
+#ifndef GAIT_LBS_NV
+#define GAIT_LBS_NV 6
+#endif
+constexpr int NA = GAIT_LBS_NA;                          // transform-blob stages (L2 latency)
+constexpr int NV = GAIT_LBS_NV;                          // v_posed stages (HBM latency); a slot is released as soon as its rows are in registers
 constexpr int NACC = 4;                                  // TMEM accumulator buffers (4 x 96 = 384 columns)
 constexpr int NG = 3;                                    // consumer groups
-constexpr int STAGE = A_BLOB + FT * V_ROW;               // 30 720 B
-constexpr int OFF_STAGE = 0;
-constexpr int OFF_JX = OFF_STAGE + NS * STAGE;           // NG x 128 floats of the fused regressor row
-constexpr int OFF_BAR = OFF_JX + NG * VT * 4;
-constexpr int SMEM3 = OFF_BAR + 256;
+static_assert(NV % NG == 0, "a consumer group must meet every phase of the v_posed barriers it waits on");
+constexpr int V_STAGE = FT * V_ROW;                      // 12 288 B
+constexpr int OFF_A = 0;
+constexpr int OFF_V = OFF_A + NA * A_BLOB;
+constexpr int OFF_BAR = OFF_V + NV * V_STAGE;
+constexpr int N_BARS = 2 * NA + 2 * NV + 2 * NACC + 4;
+constexpr int SMEM3 = OFF_BAR + ((N_BARS * 8 + 8 + 127) / 128) * 128;
+static_assert(SMEM3 <= 232448, "shared memory budget");
 constexpr int TMEM_COLS3 = 512;                          // 384 accumulator columns + 2 x 48 weight columns -> 512
 constexpr int TMEM_W = NACC * NCOL;                      // first column of the weight operand: 2 buffers x [hi 24 | lo 24]
 constexpr int W_COLS = 2 * NJ;
 constexpr int NCOMPUTE = NG * 128;
-constexpr int THREADS3 = NCOMPUTE + 64 + 128;            // + producer warp, MMA warp, weight-loader warpgroup
+constexpr int W_PROD_A = NCOMPUTE / 32;                  // warp roles after the consumer warps
+constexpr int W_MMA = NCOMPUTE / 32 + 1;
+constexpr int W_PROD_V = NCOMPUTE / 32 + 2;
+constexpr int W_LOADER = NCOMPUTE / 32 + 4;              // 4 warps (aligned to a warpgroup: TMEM lane quarter = warp & 3)
+constexpr int THREADS3 = NCOMPUTE + 128 + 128;           // + {A producer, MMA, V producer, idle} + weight-loader warpgroup
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -152,6 +171,39 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Work-item order.  Items are walked tile-major inside super-blocks of GB frame groups: (super-block, vertex tile, group).
+// A CTA's contiguous item range then stays inside one vertex tile for ~47 items (the tile's weights are loaded into tensor
+// memory once), and the transform blobs of a super-block (GB x 18 KB = 9.4 MB) stay L2-resident while the 54 tiles sweep
+// over them; with one block spanning all frames the 37.7 MB of blobs of a 16 384-frame launch were evicted by the
+// v_posed / verts streams between sweeps (4.7 -> 4.1 TB/s).  Up to GB groups (4096 frames) the order is plain tile-major.
+constexpr int GB = 512;
+struct ItemCursor {
+    int tile, g, g_begin, g_end, tiles, groups;
+    __device__ __forceinline__ void init(int item, int tiles_, int groups_) {
+        tiles = tiles_; groups = groups_;
+        const int per_block = tiles * GB;
+        const int sb = item / per_block, rem = item - sb * per_block;
+        g_begin = sb * GB;
+        g_end = min(g_begin + GB, groups);
+        const int gc = g_end - g_begin;
+        tile = rem / gc;
+        g = g_begin + rem % gc;
+    }
+    __device__ __forceinline__ void next() {
+        if (++g == g_end) {
+            g = g_begin;
+            if (++tile == tiles) {
+                tile = 0;
+                g_begin = g_end;
+                g_end = min(g_begin + GB, groups);
+                g = g_begin;
+            }
+        }
+    }
+    // last item of this CTA's walk that uses the current tile's weights
+    __device__ __forceinline__ bool last_of_tile() const { return g + 1 == g_end; }
+};
+
 // MESH = false is the joints-only variant (BASELINE config 5): the skinned vertices never leave the SM; only the `n_lm`
 // landmark vertices lm_idx[] the joint sets need are written, to lm_out (F, n_lm, 3), next to the fused regressor row.
 template <bool HAS_JX, bool MESH>
@@ -159,27 +211,34 @@ __global__ void __launch_bounds__(THREADS3, 1)
 smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restrict__ Aop,
                    const float* __restrict__ Wpack, const float* __restrict__ jx, float* __restrict__ verts,
                    float* __restrict__ jx_partial, const int32_t* __restrict__ lm_idx, int n_lm,
-                   float* __restrict__ lm_out, int F, int V, int groups, int n_items) {
+                   float* __restrict__ lm_out, int F, int V, int groups, int tiles, int n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
-    auto FULL = [&](int s) { return bar0 + 8u * s; };               // TMA landed (tx count)
-    auto EMPTY = [&](int s) { return bar0 + 8u * (NS + s); };       // consumer group done with the stage
-    auto MMAD = [&](int a) { return bar0 + 8u * (2 * NS + a); };    // accumulator a ready
-    auto ACCFREE = [&](int a) { return bar0 + 8u * (2 * NS + NACC + a); };   // accumulator a has been read out
-    auto WFULL = [&](int b) { return bar0 + 8u * (2 * NS + 2 * NACC + b); };     // weight tile b is in tensor memory
-    auto WFREE = [&](int b) { return bar0 + 8u * (2 * NS + 2 * NACC + 2 + b); }; // the MMAs that read weight buffer b have retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * (2 * NS + 2 * NACC + 4));
+    auto FULL_A = [&](int s) { return bar0 + 8u * s; };             // transform blob landed (tx count)
+    auto EMPTY_A = [&](int s) { return bar0 + 8u * (NA + s); };     // the MMAs that read it have retired
+    auto FULL_V = [&](int s) { return bar0 + 8u * (2 * NA + s); };  // v_posed rows landed (tx count)
+    auto EMPTY_V = [&](int s) { return bar0 + 8u * (2 * NA + NV + s); };     // consumer group done with the slot
+    auto MMAD = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NV + a); };    // accumulator a ready
+    auto ACCFREE = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NV + NACC + a); };   // accumulator a has been read out
+    auto WFULL = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NV + 2 * NACC + b); };     // weight tile b is in tensor memory
+    auto WFREE = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NV + 2 * NACC + 2 + b); }; // the MMAs that read weight buffer b have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * N_BARS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // contiguous, balanced item range of this CTA; item = tile * groups + group
     const int item_lo = (int)(((int64_t)n_items * blockIdx.x) / gridDim.x);
     const int item_hi = (int)(((int64_t)n_items * (blockIdx.x + 1)) / gridDim.x);
-    const int tile_lo = item_lo / groups, g_lo = item_lo % groups;
+    ItemCursor cur0;
+    cur0.init(item_lo, tiles, groups);
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(FULL(s)) : "memory");   // two issuing lanes
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY(s)), "r"(4) : "memory");    // one arrival per consumer warp
+        for (int s = 0; s < NA; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(FULL_A(s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(EMPTY_A(s)) : "memory");           // tcgen05.commit
+        }
+        for (int s = 0; s < NV; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(FULL_V(s)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY_V(s)), "r"(4) : "memory");  // one arrival per consumer warp
         }
         for (int a = 0; a < NACC; ++a) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(a)) : "memory");
@@ -191,7 +250,7 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == NCOMPUTE / 32 + 1) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS3) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -200,36 +259,57 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == NCOMPUTE / 32) {
-        // ---------------------------------------------------------------- producer (warp-uniform loop, one lane per copy)
-        int tile = tile_lo, g = g_lo;
-        for (int n = 0; n < item_hi - item_lo; ++n) {
-            const int s = n % NS;
-            if (n >= NS) mbar_wait(EMPTY(s), ((n / NS) - 1) & 1);
-            const uint32_t st = smem_u32(smem + OFF_STAGE + s * STAGE);
-            // A thread's TMA operations execute one after the other (~500 cycles each, scripts/microbench/tma_issue.cu);
-            // different lanes overlap, so each copy of an item is issued by its own lane.
+    if (warp == W_PROD_A) {
+        // ---------------------------------------------------------------- transform-blob producer (one elected lane)
+        ItemCursor c = cur0;
+        for (int n = 0; n < item_hi - item_lo; ++n, c.next()) {
+            const int s = n % NA;
+            if (n >= NA) mbar_wait(EMPTY_A(s), ((n / NA) - 1) & 1);
             if (lane == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)A_BLOB) : "memory");
-                bulk_g2s(st, Aop + (int64_t)g * (A_BLOB / 4), A_BLOB, FULL(s));
-            } else if (lane == 1) {
-                // 8 rows x 1536 B of v_posed as one 2D tensor copy (64-bit elements; rows past F read as zero)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL(s)), "r"((uint32_t)(FT * V_ROW)) : "memory");
-                asm volatile(
-                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                    ::"r"(st + A_BLOB), "l"(reinterpret_cast<uint64_t>(&tmV)), "r"(tile * (VT * 3 / 2)), "r"(g * FT), "r"(FULL(s)) : "memory");
+#ifdef GAIT_LBS_EXP_NOA      // timing experiment only (wrong results): the transform blobs are loaded for the first NA items only
+                if (n >= NA) { mbar_arrive(FULL_A(s)); } else
+#endif
+                {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL_A(s)), "r"((uint32_t)A_BLOB) : "memory");
+                bulk_g2s(smem_u32(smem + OFF_A + s * A_BLOB), Aop + (int64_t)c.g * (A_BLOB / 4), A_BLOB, FULL_A(s));
+                }
             }
             __syncwarp();
-            if (++g == groups) { g = 0; ++tile; }
         }
-    } else if (warp >= NCOMPUTE / 32 + 2) {
+    } else if (warp == W_PROD_V) {
+        // ---------------------------------------------------------------- v_posed producer: runs up to NV items ahead
+        ItemCursor c = cur0;
+        for (int n = 0; n < item_hi - item_lo; ++n, c.next()) {
+            const int s = n % NV;
+            if (n >= NV) mbar_wait(EMPTY_V(s), ((n / NV) - 1) & 1);
+            if (lane == 0) {
+#ifdef GAIT_LBS_EXP_NOV      // timing experiment only (wrong results): v_posed rows are loaded for the first NV items only
+                if (n >= NV) { mbar_arrive(FULL_V(s)); } else
+#endif
+                // 8 rows x 1536 B of v_posed as one 2D tensor copy (64-bit elements; rows past F read as zero)
+                {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(FULL_V(s)), "r"((uint32_t)V_STAGE) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                    ::"r"(smem_u32(smem + OFF_V + s * V_STAGE)), "l"(reinterpret_cast<uint64_t>(&tmV)), "r"(c.tile * (VT * 3 / 2)),
+                      "r"(c.g * FT), "r"(FULL_V(s)) : "memory");
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp >= W_LOADER) {
         // ---------------------------------------------------------------- weight loader: vertex tile -> tensor memory
         // The skinning weights are the M-side operand of every MMA of a vertex tile (~46 work items per CTA), so
         // they live in tensor memory (lane = vertex, columns [hi 24 | lo 24]) instead of being re-read from shared
         // memory by each of the 9 MMAs of each item.  Two buffers: the next tile is loaded while the current one is used.
         const int row = (warp & 3) * 32 + lane;                    // TMEM lane = vertex within the tile
-        const int tile_hi = (item_hi - 1) / groups;
-        for (int tile = tile_lo, i = 0; tile <= tile_hi && item_hi > item_lo; ++tile, ++i) {
+        ItemCursor c = cur0;
+        int cur_tile = -1, i = -1;
+        for (int n = 0; n < item_hi - item_lo; ++n, c.next()) {
+            if (c.tile == cur_tile) continue;          // same rule as the MMA issuer: one load per run of items of a tile
+            cur_tile = c.tile;
+            ++i;
+            const int tile = c.tile;
             const int b = i & 1;
             if (i >= 2) mbar_wait(WFREE(b), ((i >> 1) - 1) & 1);
             const float* blob = Wpack + (int64_t)tile * (W_BLOB / 4);
@@ -249,14 +329,16 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(WFULL(b));
         }
-    } else if (warp == NCOMPUTE / 32 + 1) {
+    } else if (warp == W_MMA) {
         // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
         constexpr uint32_t A_LBO = NCOL * 16, SBO = 128;
-        int cur_tile = -1, widx = -1, tile = tile_lo, g = g_lo;
+        int cur_tile = -1, widx = -1;
+        ItemCursor c = cur0;
         const int n_total = item_hi - item_lo;
         for (int n = 0; n < n_total; ++n) {
-            const int s = n % NS;
+            const int s = n % NA;
+            const int tile = c.tile;
             if (tile != cur_tile) {
                 ++widx;
                 mbar_wait(WFULL(widx & 1), (widx >> 1) & 1);
@@ -264,12 +346,14 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             }
             const int a = n % NACC;
             if (n >= NACC) mbar_wait(ACCFREE(a), ((n / NACC) - 1) & 1);
-            mbar_wait(FULL(s), (n / NS) & 1);
+            mbar_wait(FULL_A(s), (n / NA) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(smem + OFF_STAGE + s * STAGE), a_lo = a_hi + A_PART;
+            const uint32_t a_hi = smem_u32(smem + OFF_A + s * A_BLOB), a_lo = a_hi + A_PART;
             const uint32_t acc = tmem_d + (uint32_t)(a * NCOL);
             const uint32_t w_hi = tmem_d + (uint32_t)(TMEM_W + (widx & 1) * W_COLS), w_lo = w_hi + NJ;
-            const bool last_of_tile = (g + 1 == groups) || (n + 1 == n_total);
+            ItemCursor nx = c;
+            nx.next();
+            const bool last_of_tile = (n + 1 == n_total) || nx.tile != tile;
             if (elect_one()) {
                 // D[128 x 96] = W(128 x 24, tensor memory) . Aop(96 x 24, shared memory)^T, split-TF32: small cross terms first
 #pragma unroll
@@ -282,116 +366,152 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(a)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(EMPTY_A(s)) : "memory");
                 if (last_of_tile)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(WFREE(widx & 1)) : "memory");
             }
             __syncwarp();
-            if (++g == groups) { g = 0; ++tile; }
+            c = nx;
         }
     } else if (warp < NCOMPUTE / 32) {
         // ---------------------------------------------------------------- consumer groups
+        // Thread = vertex (TMEM lane).  Everything an item needs is pulled into registers at once - the 96 accumulator
+        // columns (T for 8 frames) and the vertex's 8 v_posed entries - after which the accumulator and the v_posed slot
+        // are released immediately; the skinned vertex is stored straight from registers (three 4-byte stores per frame,
+        // a warp covering 384 contiguous bytes: the sectors are completed in L2).  The earlier version staged the result
+        // in shared memory for 8-byte stores and read it back for the regressor row: ~430 instead of ~220 warp
+        // instructions per item in a kernel that is bound by its instruction-issue latency chain, not by bytes.
         const int grp = warp >> 2, quad = warp & 3;                // group, TMEM lane quarter
         const int gt = tid & 127;                                  // thread within the group = vertex within the tile
-        float* sJx = reinterpret_cast<float*>(smem + OFF_JX) + grp * VT;
-        int cur_tile = -1, tile = tile_lo, g = g_lo + grp;
-        while (g >= groups) { g -= groups; ++tile; }
+        int cur_tile = -1;
+        float wjx = 0.f;
+        bool any_jx = false;
+        int lm_slot = -1, lm_count = 0;
+        ItemCursor c = cur0;
+        for (int k = 0; k < grp; ++k) c.next();
         for (int n = grp; n < item_hi - item_lo; n += NG) {
-            const int s = n % NS;
-            const uint32_t ph = (n / NS) & 1;
+            const int s = n % NV;
+            const int tile = c.tile, g = c.g;
+            const uint32_t ph = (n / NV) & 1;
             const int v0 = tile * VT, nv = min(VT, V - v0);
             const int f0 = g * FT, nf = min(FT, F - f0);
-            float* sV = reinterpret_cast<float*>(smem + OFF_STAGE + s * STAGE + A_BLOB);
-            if (HAS_JX && tile != cur_tile) {
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");    // previous tile's partial pass finished
-                sJx[gt] = (gt < nv) ? jx[v0 + gt] : 0.f;
+            const float* sV = reinterpret_cast<const float*>(smem + OFF_V + s * V_STAGE);
+            if (tile != cur_tile) {
                 cur_tile = tile;
+                if (HAS_JX) {
+                    // regressor-row weight of this thread's vertex; rows of a real SMPL regressor are sparse, and a warp
+                    // whose 32 vertices all have weight 0 skips the reduction (it contributes exact zeros)
+                    wjx = (gt < nv) ? jx[v0 + gt] : 0.f;
+                    any_jx = __any_sync(0xffffffffu, wjx != 0.f);
+                }
+                if (!MESH || lm_out) {
+                    lm_slot = -1; lm_count = 0;
+                    if (gt < nv)
+                        for (int l = 0; l < n_lm; ++l)
+                            if (lm_idx[l] == v0 + gt) { if (lm_count == 0) lm_slot = l; ++lm_count; }
+                }
             }
             const int a = n % NACC;
-            mbar_wait(FULL(s), ph);                                // v_posed rows visible
+            mbar_wait(FULL_V(s), ph);                              // v_posed rows visible
             mbar_wait(MMAD(a), (n / NACC) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            {
-                // all 96 accumulator columns of this vertex and its 8 v_posed entries are fetched up front
-                // (one TMEM round trip, one smem round trip), then 8 independent 3x4 applies
-                uint32_t t[NCOL];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * NCOL);
-                tmem_ld32_nowait(taddr, t);
-                tmem_ld32_nowait(taddr + 32, t + 32);
-                tmem_ld32_nowait(taddr + 64, t + 64);
-                float vx[FT], vy[FT], vz[FT];
-                float* p = sV + gt * 3;
+            uint32_t t[NCOL];
+            const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * NCOL);
+            tmem_ld32_nowait(taddr, t);
+            tmem_ld32_nowait(taddr + 32, t + 32);
+            tmem_ld32_nowait(taddr + 64, t + 64);
+            float vx[FT], vy[FT], vz[FT];
+            const float* p = sV + gt * 3;
 #pragma unroll
-                for (int f = 0; f < FT; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ACCFREE(a));            // the accumulator can take the MMAs of item n + NACC
-#pragma unroll
-                for (int f = 0; f < FT; ++f) {
-                    const uint32_t* q = t + f * 12;
-                    const float x = vx[f], y = vy[f], z = vz[f];
-                    p[f * (VT * 3)] = __uint_as_float(q[0]) * x + __uint_as_float(q[1]) * y + __uint_as_float(q[2]) * z + __uint_as_float(q[3]);
-                    p[f * (VT * 3) + 1] = __uint_as_float(q[4]) * x + __uint_as_float(q[5]) * y + __uint_as_float(q[6]) * z + __uint_as_float(q[7]);
-                    p[f * (VT * 3) + 2] = __uint_as_float(q[8]) * x + __uint_as_float(q[9]) * y + __uint_as_float(q[10]) * z + __uint_as_float(q[11]);
-                }
-            }
+            for (int f = 0; f < FT; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // the whole tile is in smem
-            const int n2 = (nv * 3) >> 1;
+            // the smem values must have arrived before the slot is handed back to the TMA producer
+            asm volatile("" ::"f"(vx[FT - 1]), "f"(vy[FT - 1]), "f"(vz[FT - 1]) : "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(ACCFREE(a));                           // the accumulator can take the MMAs of item n + NACC
+                mbar_arrive(EMPTY_V(s));                           // the slot can take the rows of item n + NV
+            }
+            float ox[FT], oy[FT], oz[FT];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int f = quad + 4 * h;                        // warp q handles frames q and q+4
-                if (f < nf) {
-                    const float* row = sV + f * (VT * 3);
-                    if (HAS_JX) {
-                        // partial dot product of the regressor row with this tile's skinned vertices
-                        float a = 0.f, bb = 0.f, c = 0.f;
+            for (int f = 0; f < FT; ++f) {
+                const uint32_t* q = t + f * 12;
+                const float x = vx[f], y = vy[f], z = vz[f];
+                ox[f] = __uint_as_float(q[0]) * x + __uint_as_float(q[1]) * y + __uint_as_float(q[2]) * z + __uint_as_float(q[3]);
+                oy[f] = __uint_as_float(q[4]) * x + __uint_as_float(q[5]) * y + __uint_as_float(q[6]) * z + __uint_as_float(q[7]);
+                oz[f] = __uint_as_float(q[8]) * x + __uint_as_float(q[9]) * y + __uint_as_float(q[10]) * z + __uint_as_float(q[11]);
+            }
+            if (MESH && gt < nv) {
+                float* dst = verts + ((int64_t)f0 * V + v0 + gt) * 3;
 #pragma unroll
-                        for (int i = 0; i < VT / 32; ++i) {
-                            const int v = lane + 32 * i;
-                            const float w = sJx[v];
-                            a = fmaf(w, row[v * 3], a); bb = fmaf(w, row[v * 3 + 1], bb); c = fmaf(w, row[v * 3 + 2], c);
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            a += __shfl_xor_sync(0xffffffffu, a, o);
-                            bb += __shfl_xor_sync(0xffffffffu, bb, o);
-                            c += __shfl_xor_sync(0xffffffffu, c, o);
-                        }
-                        if (lane == 0) {
-                            float* o = jx_partial + ((int64_t)tile * F + f0 + f) * 3;
-                            o[0] = a; o[1] = bb; o[2] = c;
-                        }
+                for (int f = 0; f < FT; ++f)
+                    if (f < nf) {
+                        float* d = dst + (int64_t)f * V * 3;
+                        d[0] = ox[f]; d[1] = oy[f]; d[2] = oz[f];
                     }
-                    if (MESH) {
-                        // coalesced stores: nv*3 contiguous floats per frame, 8-byte aligned (V even, v0*12 % 8 == 0)
-                        float2* dst = reinterpret_cast<float2*>(verts + ((int64_t)(f0 + f) * V + v0) * 3);
-                        const float2* src = reinterpret_cast<const float2*>(row);
+            }
+            if ((!MESH || lm_out) && lm_count > 0) {
+                // landmark vertices (the only output in joints-only mode; next to a mesh that goes to peer memory they keep
+                // the joint assembly's reads local)
+                for (int l = lm_slot; l < n_lm; ++l) {
+                    if (l != lm_slot && lm_idx[l] != v0 + gt) continue;
 #pragma unroll
-                        for (int i = 0; i < 6; ++i)
-                            if (lane + 32 * i < n2) dst[lane + 32 * i] = src[lane + 32 * i];
-                    } else {
-                        // landmark vertices of this tile only
-                        for (int l = lane; l < n_lm; l += 32) {
-                            const int lv = lm_idx[l] - v0;
-                            if (lv >= 0 && lv < nv) {
-                                float* o = lm_out + ((int64_t)(f0 + f) * n_lm + l) * 3;
-                                o[0] = row[lv * 3]; o[1] = row[lv * 3 + 1]; o[2] = row[lv * 3 + 2];
-                            }
+                    for (int f = 0; f < FT; ++f)
+                        if (f < nf) {
+                            float* o = lm_out + ((int64_t)(f0 + f) * n_lm + l) * 3;
+                            o[0] = ox[f]; o[1] = oy[f]; o[2] = oz[f];
                         }
-                    }
+                    if (lm_count == 1) break;
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic accesses precede the stage's TMA refill
-            __syncwarp();
-            if (lane == 0) mbar_arrive(EMPTY(s));
-            g += NG;
-            while (g >= groups) { g -= groups; ++tile; }
+            if (HAS_JX) {
+                // partial of the regressor row over this warp's 32 vertices: 24 sums (8 frames x 3) reduced with a transposed
+                // butterfly - at every level a lane keeps one half of its values and sends the other - 24 shuffles in all;
+                // afterwards lane l holds the sum for frame 4*b4 + 2*b3 + b2 (b = bits of l), component (l & 3), lanes with (l & 3) == 3 idle
+                float r = 0.f;
+                if (any_jx) {
+                    float P[24];
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) { P[f * 3] = wjx * ox[f]; P[f * 3 + 1] = wjx * oy[f]; P[f * 3 + 2] = wjx * oz[f]; }
+                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+                    float Q[12], R6[6], S[4], U[2];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        const float send = b16 ? P[i] : P[i + 12], keep = b16 ? P[i + 12] : P[i];
+                        Q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const float send = b8 ? Q[i] : Q[i + 6], keep = b8 ? Q[i + 6] : Q[i];
+                        R6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float send = b4 ? R6[i] : R6[i + 3], keep = b4 ? R6[i + 3] : R6[i];
+                        S[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    S[3] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float send = b2 ? S[i] : S[i + 2], keep = b2 ? S[i + 2] : S[i];
+                        U[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    {
+                        const float send = b1 ? U[0] : U[1], keep = b1 ? U[1] : U[0];
+                        r = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                    }
+                }
+                const int pf = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1), pc = lane & 3;
+                if (pc < 3 && pf < nf) jx_partial[((int64_t)(tile * 4 + quad) * F + f0 + pf) * 3 + pc] = r;
+            }
+#pragma unroll
+            for (int k = 0; k < NG; ++k) c.next();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == NCOMPUTE / 32 + 1) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS3) : "memory");
     }
 }
@@ -417,6 +537,8 @@ int gait_smpl_lbs_pack(const float* lbs_weights, float* packed, int64_t V, gait_
     return check_launch("smpl_lbs_pack");
 }
 
+int64_t gait_smpl_lbs_jx_parts(int64_t V) { return V <= 0 ? 0 : 4 * ceil_div(V, lbs::VT); }
+
 size_t gait_smpl_lbs_aop_bytes(int64_t F) {
     return F <= 0 ? 0 : (size_t)ceil_div(F, lbs::FT) * lbs::A_BLOB;
 }
@@ -428,7 +550,8 @@ static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, co
     if (F == 0 || V == 0) return GAIT_OK;
     const bool mesh = verts != nullptr;
     GAIT_REQUIRE(v_posed && Aop && Wpack, "smpl_lbs_tc: null pointer");
-    GAIT_REQUIRE(mesh || (lm_out && lm_idx && n_lm > 0), "smpl_lbs_tc: neither a mesh nor a landmark output given");
+    GAIT_REQUIRE(mesh || lm_out, "smpl_lbs_tc: neither a mesh nor a landmark output given");
+    GAIT_REQUIRE(!lm_out || (lm_idx && n_lm > 0 && n_lm <= 1024), "smpl_lbs_tc: landmark output needs 1..1024 landmark ids");
     GAIT_REQUIRE((jx == nullptr) == (jx_partial == nullptr), "smpl_lbs_tc: jx and jx_partial go together");
     GAIT_REQUIRE((V & 1) == 0 && (!mesh || aligned8(verts)), "smpl_lbs_tc: V must be even and verts 8-byte aligned");
     const int64_t tiles = ceil_div(V, lbs::VT);
@@ -459,7 +582,7 @@ static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, co
                                 lbs::VT * 3 / 2, lbs::FT, false));
 #define GAIT_LBS_LAUNCH(JX, MESH)                                                                                       \
     lbs::smpl_lbs_tc_kernel<JX, MESH><<<grid, lbs::THREADS3, lbs::SMEM3, stream>>>(                                       \
-        tmV, Aop, Wpack, jx, verts, jx_partial, lm_idx, n_lm, lm_out, (int)F, (int)V, (int)groups, (int)n_items)
+        tmV, Aop, Wpack, jx, verts, jx_partial, lm_idx, n_lm, lm_out, (int)F, (int)V, (int)groups, (int)tiles, (int)n_items)
     if (jx && mesh) GAIT_LBS_LAUNCH(true, true);
     else if (jx) GAIT_LBS_LAUNCH(true, false);
     else if (mesh) GAIT_LBS_LAUNCH(false, true);
@@ -472,6 +595,12 @@ int gait_smpl_lbs_tc(const float* v_posed, int64_t ldv, const float* Aop, const 
                      float* verts, float* jx_partial, int64_t F, int64_t V, gait_stream_t stream) {
     GAIT_REQUIRE(verts != nullptr || (F == 0 || V == 0), "smpl_lbs_tc: null pointer");
     return lbs_tc_launch(v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, nullptr, 0, nullptr, F, V, as_stream(stream));
+}
+
+int gait_smpl_lbs_tc_ex(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
+                        float* verts, float* jx_partial, const int32_t* lm_idx, int n_lm, float* lm_out, int64_t F,
+                        int64_t V, gait_stream_t stream) {
+    return lbs_tc_launch(v_posed, ldv, Aop, Wpack, jx, verts, jx_partial, lm_idx, n_lm, lm_out, F, V, as_stream(stream));
 }
 
 int gait_smpl_lbs_tc_joints(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,

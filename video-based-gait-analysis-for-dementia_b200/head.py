@@ -68,7 +68,10 @@ class GaitHead(nn.Module):
         self._slots, self._graphs = [], []
 
     # ------------------------------------------------------------------ buffers for one (S,T)
-    def _make_plan(self, S: int, T: int):
+    def _make_plan(self, S: int, T: int, verts_addr: int | None = None):
+        """Buffers of one (S,T) step.  verts_addr: raw device address that receives the mesh (F,V,3) instead of the plan's own
+        output buffer - a slice of a gathered buffer, possibly PEER memory of the root rank (sharding.RootGather): the
+        skinning kernel then also writes the landmark vertices to a local buffer, so that nothing reads the remote mesh."""
         dev = self.regressor.fc1.weight.device
         if dev.type != "cuda":
             raise L.GaitLibraryError("GaitHead is on %s; move it to a CUDA device (no CPU path)" % dev)
@@ -88,17 +91,27 @@ class GaitHead(nn.Module):
             "aop": e(lib.gait_smpl_lbs_aop_bytes(F) // 4),
             "coef": e(F, 224), "v_posed": e(F, 384 * ((V + 127) // 128)),
             # full mesh (F,V,3), or in joints-only mode just the landmark vertices the joint sets read (config 5)
-            "verts": None,
-            "lm_verts": None if self.write_mesh else e(F, self.regressor.smpl._prepare()["n_landmarks"], 3),
-            "lm_iota": None if self.write_mesh else torch.arange(self.regressor.smpl._prepare()["n_landmarks"], dtype=torch.int32, device=dev),
-            "extra": e((V + 127) // 128, F, 1, 3),
-            # every output of a step lives in ONE buffer [mesh | small per-frame outputs], so the host copy is one transfer
-            "outbuf": e(self._mesh_floats(F, V) + _small_layout(F)[1]),
+            "verts": None, "verts_addr": None,
+            "extra": e(4 * ((V + 127) // 128), F, 1, 3),      # gait_smpl_lbs_jx_parts(V) partial sums of the thorax row
             "gather": torch.tensor(SPIN2_TO_KINECTV2, dtype=torch.int32, device=dev),
         }
-        nm = self._mesh_floats(F, V)
-        if self.write_mesh:
+        if verts_addr is not None and not self.write_mesh:
+            raise L.GaitLibraryError("verts_addr given to a joints-only head")
+        external = verts_addr is not None
+        local_lm = external or not self.write_mesh
+        n_lm = self.regressor.smpl._prepare()["n_landmarks"]
+        p["lm_verts"] = e(F, n_lm, 3) if local_lm else None
+        p["lm_iota"] = torch.arange(n_lm, dtype=torch.int32, device=dev) if local_lm else None
+        # every output of a step lives in ONE buffer [mesh | small per-frame outputs], so the host copy is one transfer
+        nm = 0 if external else self._mesh_floats(F, V)
+        p["outbuf"] = e(nm + _small_layout(F)[1])
+        if external:
+            if verts_addr % 8:
+                raise L.GaitLibraryError("verts_addr must be 8-byte aligned")
+            p["verts_addr"] = int(verts_addr)
+        elif self.write_mesh:
             p["verts"] = p["outbuf"][:F * V * 3].view(F, V, 3)
+            p["verts_addr"] = p["verts"].data_ptr()
         p["small"] = p["outbuf"][nm:]
         for key, _, shape, off, n in _small_layout(F)[0]:
             p[key] = p["small"][off:off + n].view(F, *shape)
@@ -166,17 +179,18 @@ class GaitHead(nn.Module):
                 ptr(p["theta"]), F, st())),
             ("blend", lambda: call(
                 "gait_smpl_blend", ptr(p["coef"]), ptr(sk["basis_t"]), ptr(p["v_posed"]), sk["ldv"], F, 3 * V, st())),
-            ("lbs", (lambda: call(
-                "gait_smpl_lbs_tc", ptr(p["v_posed"]), sk["ldv"], ptr(p["aop"]), ptr(sk["lbs_wpack"]),
-                ptr(sk["extra_thorax"]), ptr(p["verts"]), ptr(p["extra"]), F, V, st())) if self.write_mesh else (lambda: call(
-                "gait_smpl_lbs_tc_joints", ptr(p["v_posed"]), sk["ldv"], ptr(p["aop"]), ptr(sk["lbs_wpack"]),
-                ptr(sk["extra_thorax"]), ptr(p["extra"]), ptr(sk["landmarks"]), sk["n_landmarks"], ptr(p["lm_verts"]),
-                F, V, st()))),
+            # mesh to p["verts_addr"] (own buffer, or an external / peer address together with local landmark vertices),
+            # or landmark vertices only (joints-only mode)
+            ("lbs", lambda: call(
+                "gait_smpl_lbs_tc_ex", ptr(p["v_posed"]), sk["ldv"], ptr(p["aop"]), ptr(sk["lbs_wpack"]),
+                ptr(sk["extra_thorax"]), p["verts_addr"], ptr(p["extra"]),
+                ptr(sk["landmarks"]) if p["lm_verts"] is not None else None, sk["n_landmarks"] if p["lm_verts"] is not None else 0,
+                ptr(p["lm_verts"]), F, V, st())),
             ("joints", (lambda: call(
-                "gait_joints_assemble", ptr(p["Jp"]), ptr(p["verts"]), V, ptr(sk["landmarks"]), sk["n_landmarks"],
+                "gait_joints_assemble", ptr(p["Jp"]), p["verts_addr"], V, ptr(sk["landmarks"]), sk["n_landmarks"],
                 ptr(p["extra"]), 1, sk["vtiles"], F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
                 5000., 224., 112.,
-                ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st())) if self.write_mesh else (lambda: call(
+                ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st())) if p["lm_verts"] is None else (lambda: call(
                 "gait_joints_assemble", ptr(p["Jp"]), ptr(p["lm_verts"]), sk["n_landmarks"], ptr(p["lm_iota"]), sk["n_landmarks"],
                 ptr(p["extra"]), 1, sk["vtiles"], F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
                 5000., 224., 112.,
@@ -235,31 +249,38 @@ class GaitHead(nn.Module):
             best = min(best, a.elapsed_time(b) / launches)
         return best
 
+    def capture_plan(self, p, warm: bool = True):
+        """Capture one step over the buffers of plan `p` into a CUDA graph (returns it; sets launches_per_step)."""
+        if warm:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._launch(p)                  # warm-up outside capture (lazy module loading)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+        n0 = L.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch(p)
+        self.launches_per_step = L.launch_count() - n0
+        return g
+
     def capture(self, S: int, T: int, slots: int = 1):
         """Plan buffers for (S,T) and capture one step per slot into a CUDA graph."""
         self.plan(S, T, slots)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            self._launch(self._slots[0])         # warm-up outside capture (lazy module loading)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
         for i, p in enumerate(self._slots):
-            n0 = L.launch_count()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._launch(p)
-            self.launches_per_step = L.launch_count() - n0
-            self._graphs[i] = g
+            self._graphs[i] = self.capture_plan(p, warm=(i == 0))
         self._graph = self._graphs[0]
         return self._graph
 
     @torch.no_grad()
-    def run_host_batches(self, inputs, outputs):
+    def run_host_batches(self, inputs, outputs, sync: bool = True):
         """End-to-end path for HOST data: for every batch, pinned features (S,T,2048) -> H2D -> one step ->
         D2H of every output into the matching dict of pinned host tensors.  With two planned slots the
         three phases of consecutive batches overlap on separate streams (copy-in, compute, copy-out);
-        returns after the last D2H has completed.  `outputs[i]` needs the keys of self.outputs()."""
+        with sync=True (default) the host waits for the last D2H of every slot before returning, so the pinned outputs may
+        be read right away; sync=False only orders the current stream after the copies (the caller synchronises).
+        `outputs[i]` needs the keys of self.outputs()."""
         if self._plan is None:
             raise L.GaitLibraryError("call plan()/capture() first")
         ns = len(self._slots)
@@ -298,6 +319,10 @@ class GaitHead(nn.Module):
                 ev_out[k] = s_out.record_event()
         cur.wait_stream(s_out)
         cur.wait_stream(s_in)
+        if sync:
+            for ev in ev_out:
+                if ev is not None:
+                    ev.synchronize()             # the host may read outputs[...] as soon as this returns
 
     def outputs(self, slot: int = 0):
         p = self._slots[slot]
@@ -305,7 +330,7 @@ class GaitHead(nn.Module):
         v = lambda t: t.view(S, T, *t.shape[1:])
         out = {"theta": v(p["theta"]), "kp_2d": v(p["kp2d"]), "kp_3d": v(p["joints"]), "rotmat": v(p["rotmat"]),
                "kinect25": v(p["kinect"])}
-        if self.write_mesh:
+        if p["verts"] is not None:               # absent in joints-only mode and when the mesh goes to an external address
             out["verts"] = v(p["verts"])
         return out
 

@@ -22,9 +22,7 @@ _STATE_LD = 160
 def _regress_joints(J_regressor, verts, subset14):
     """pare.py:70-76 / spin.py:279-282: (J',V).(F,V,3), then optional H36M_TO_J14 pick."""
     Jr = L.f32(J_regressor.to(verts.device), "J_regressor")
-    F, V = verts.shape[0], verts.shape[1]
-    out = torch.empty(F, Jr.shape[0], 3, device=verts.device)
-    L.call("gait_joint_regress", L.ptr(verts), L.ptr(Jr), L.ptr(out), F, V, Jr.shape[0], L.stream_ptr())
+    out = L.joint_regress(verts, Jr)
     if subset14:
         out = out[:, H36M_TO_J14, :]
     return out

@@ -172,7 +172,8 @@ class SMPL(nn.Module):
             "parents": self.parents.to(torch.int32).contiguous(),
             "lbs_weights": lbs_w,
             "lbs_wpack": wpack,                                           # tensor-core LBS operand (lbs_tc.cu)
-            "vtiles": (V + 127) // 128, "ldv": 384 * ((V + 127) // 128),  # padded v_posed row (TMA bulk rows)
+            "vtiles": 4 * ((V + 127) // 128),   # partial sums of the fused regressor row (gait_smpl_lbs_jx_parts)
+             "ldv": 384 * ((V + 127) // 128),  # padded v_posed row (TMA bulk rows)
             "landmarks": lm, "n_landmarks": n_lm,
             "extra_all": self.J_regressor_extra.contiguous(),
             "extra_thorax": self.J_regressor_extra[_THORAX_ROW:_THORAX_ROW + 1].contiguous(),
@@ -230,7 +231,7 @@ class SMPL(nn.Module):
             if self.extra:
                 Jx, jmap = pk["extra_all"], pk["map_spin"]
                 extra = torch.empty(1, F, Jx.shape[0], 3, device=dev)
-                L.call("gait_joint_regress", L.ptr(verts), L.ptr(Jx), L.ptr(extra), F, V, Jx.shape[0], st)
+                L.joint_regress(verts, Jx, extra.view(F, Jx.shape[0], 3))          # 9 rows, one streaming pass (jreg.cu)
             else:
                 jmap = pk["map_smplx"]
         J = jmap.numel()
