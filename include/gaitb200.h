@@ -101,6 +101,15 @@ int gait_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const 
  * allocated and unchanged until gait_release_weight(W) (call it before freeing or modifying W). */
 int gait_prepare_weight(const float* W, float* W_hilo, int64_t n, gait_stream_t stream);
 int gait_release_weight(const float* W);
+/* The same with an EXPLICIT handle and no global state: gait_split_weight only writes W_hilo = [hi | lo] (2n floats) for the
+ * n floats at W_base; gait_linear_prepared is gait_linear with that operand passed in (W may point anywhere inside
+ * [W_base, W_base + n_prepared): row views of a packed weight array).  Nothing is registered, so nothing can go stale: the
+ * caller owns W_base / W_hilo and their lifetime.  (The registry above is kept for the composite entry points - GRU layer, HMR
+ * regressor, blend - and as the Python convenience, which releases entries when the owning tensor dies or moves.) */
+int gait_split_weight(const float* W_base, float* W_hilo, int64_t n, gait_stream_t stream);
+int gait_linear_prepared(const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_hilo, int64_t n_prepared,
+                         const float* W_base, const float* bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
+                         int64_t M, int64_t N, int64_t K, gait_stream_t stream);
 
 /* Debug hook: device buffer of 64*4 uint64 that receives per-k-block pipeline timestamps (stage free, data
  * landed, converted, MMAs issued) of CTA 0 of subsequent tensor-core GEMM launches; NULL disables. */

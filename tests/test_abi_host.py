@@ -206,3 +206,32 @@ def test_kinect_db_writer_format(tmp_path):
     assert np.array_equal(np.concatenate([d["joints3D"] for d in dbs]), allj)
     with pytest.raises(ValueError):
         KinectDbWriter(str(tmp_path / "db.pkl"))
+
+
+def test_strict_load_of_reference_key_set(smpl_data):
+    """batch_generation.py:210-219 loads the checkpoint with strict=True.  tests/golden/state_dict_keys.json holds key -> shape of
+    the state dicts of the reference's own spin.Regressor / pare.VPRegressor / pare.SMPLRegressor / smpl.SMPLHead (unmodified
+    source behind import stubs, tests/golden/make_golden_keys.py).  A state dict with exactly that key set must load strictly
+    into the drop-in modules.  One key is renamed: the stub that stands in for smplx registers `extra_joints_idxs` on the body
+    model itself, real smplx 0.1.26 keeps it in the `vertex_joint_selector` sub-module - the product follows smplx."""
+    import json
+    from pathlib import Path
+    from gaitb200.regressor import Regressor, SMPLRegressor, VPRegressor
+    from gaitb200.smpl import SMPLHead
+    ref = json.loads((Path(__file__).parent / "golden" / "state_dict_keys.json").read_text())
+    smpl_data = {k: np.array(v, copy=True) for k, v in smpl_data.items()}     # module buffers may alias the arrays they are built from
+    mean = synthetic.make_mean_params()
+    mods = {"spin.Regressor": Regressor(mean, smpl_data), "pare.VPRegressor": VPRegressor(smpl_model_dir=smpl_data),
+            "pare.SMPLRegressor": SMPLRegressor(smpl_model_dir=smpl_data), "smpl.SMPLHead": SMPLHead(smpl_model_dir=smpl_data)}
+    g = torch.Generator().manual_seed(0)
+    for name, mod in mods.items():
+        want = {k.replace("extra_joints_idxs", "vertex_joint_selector.extra_joints_idxs"): tuple(s) for k, s in ref[name].items()}
+        have = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+        assert have == want, (name, set(have) ^ set(want), {k: (have[k], want[k]) for k in have if k in want and have[k] != want[k]})
+        # a "checkpoint" with the reference's keys, shapes and dtypes loads strictly and lands in the module
+        ckpt = {k: (torch.randn(*s, generator=g) if v.dtype.is_floating_point else torch.zeros(*s, dtype=v.dtype))
+                for (k, s), v in zip(want.items(), [mod.state_dict()[k] for k in want])}
+        res = mod.load_state_dict(ckpt, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        k0 = next(k for k in want if k.endswith("lbs_weights"))
+        assert torch.equal(mod.state_dict()[k0], ckpt[k0])

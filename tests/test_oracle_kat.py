@@ -107,3 +107,60 @@ def test_kinect_joint_selection(smpl_data):
     assert torch.equal(so.joints[:, 24:28], so.vertices[:, picks])
     thorax = torch.from_numpy(smpl_data["J_regressor_extra"][5]) @ so.vertices
     assert torch.allclose(so.joints[:, 28], thorax, atol=1e-6)
+
+
+# ---- hand-computed three-joint chain (root -> joint 1 -> joint 4 of the SMPL tree) with two skinned vertices.
+# Rotations are about z: R0 = Rz(90), R1 = Rz(90), R4 = Rz(90); rest joints J0 = (0,0,0), J1 = (0,1,0), J4 = (0,2,0).
+#   posed joints: J0' = 0;  J1' = R0 J1 = (-1,0,0);  J4' = J1' + R0 R1 (J4 - J1) = (-1,0,0) + Rz(180)(0,1,0) = (-1,-1,0)
+#   vertex a = (0.5,1.5,0), weights 1/2 on joint 1, 1/2 on joint 4:
+#       by joint 1: Rz(180)(a - J1) + J1' = (-0.5,-0.5,0) + (-1,0,0)  = (-1.5,-0.5,0)
+#       by joint 4: Rz(270)(a - J4) + J4' = (-0.5,-0.5,0) + (-1,-1,0) = (-1.5,-1.5,0)        -> a' = (-1.5,-1.0,0)
+#   vertex b = (0.25,0.5,0.1), weights 3/4 on the root, 1/4 on joint 1:
+#       by root:    Rz(90) b              = (-0.5,0.25,0.1)
+#       by joint 1: Rz(180)(b - J1) + J1' = (-0.25,0.5,0.1) + (-1,0,0) = (-1.25,0.5,0.1)     -> b' = (-0.6875,0.3125,0.1)
+def chain_kat():
+    import math
+    parents = torch.tensor(synthetic.SMPL_PARENTS)
+    Rz = lambda d: torch.tensor([[math.cos(math.radians(d)), -math.sin(math.radians(d)), 0.],
+                                 [math.sin(math.radians(d)), math.cos(math.radians(d)), 0.], [0., 0., 1.]], dtype=torch.float64).float()
+    R = torch.eye(3).repeat(1, 24, 1, 1)
+    R[0, 0], R[0, 1], R[0, 4] = Rz(90), Rz(90), Rz(90)
+    J = torch.zeros(1, 24, 3)
+    J[0, 1] = torch.tensor([0., 1., 0.])
+    J[0, 4] = torch.tensor([0., 2., 0.])
+    for j in range(24):                      # park the other joints away from the chain; their weights are zero
+        if j not in (0, 1, 4):
+            J[0, j] = torch.tensor([3. + j, -2., 1.])
+    verts = torch.tensor([[[0.5, 1.5, 0.], [0.25, 0.5, 0.1]]])
+    W = torch.zeros(2, 24)
+    W[0, 1], W[0, 4] = 0.5, 0.5
+    W[1, 0], W[1, 1] = 0.75, 0.25
+    expect_v = torch.tensor([[[-1.5, -1.0, 0.], [-0.6875, 0.3125, 0.1]]])
+    expect_j = {0: [0., 0., 0.], 1: [-1., 0., 0.], 4: [-1., -1., 0.]}
+    return parents, R, J, verts, W, expect_v, expect_j
+
+
+def test_three_joint_chain_hand_computed():
+    parents, R, J, verts, W, expect_v, expect_j = chain_kat()
+    posed, A = OL.batch_rigid_transform(R, J, parents)
+    for j, e in expect_j.items():
+        assert torch.allclose(posed[0, j], torch.tensor(e), atol=1e-6), (j, posed[0, j])
+    Tm = torch.matmul(W.unsqueeze(0), A.view(1, 24, 16)).view(1, 2, 4, 4)
+    out = torch.matmul(Tm, torch.cat([verts, torch.ones(1, 2, 1)], 2).unsqueeze(-1))[:, :, :3, 0]
+    assert torch.allclose(out, expect_v, atol=1e-6), out
+
+
+def test_oracle_matches_independent_fp64_loops(smpl_data):
+    """oracle/smplx_lbs.py (smplx's tensor formulation) against oracle/independent_lbs.py (textbook per-vertex FP64 loops that
+    share no code with it): 2 random poses, 300 random vertices + all landmark vertices, every posed joint."""
+    from oracle.independent_lbs import pose_vertices_fp64
+    smpl = OL.SMPLX_SMPL(smpl_data)
+    rot6d, betas, _ = synthetic.make_pose_inputs(2, seed=11, noise=0.6)
+    R = OG.rot6d_to_rotmat(rot6d).view(2, 24, 3, 3)
+    so = smpl(betas=betas, body_pose=R[:, 1:], global_orient=R[:, :1], pose2rot=False)
+    rng = np.random.default_rng(3)
+    ids = np.unique(np.concatenate([rng.choice(6890, 300, replace=False), np.asarray(smpl_data["landmark_verts"])]))
+    for f in range(2):
+        v64, j64 = pose_vertices_fp64(smpl_data, betas[f].numpy(), R[f].numpy(), ids)
+        assert np.abs(so.vertices[f, ids].numpy() - v64).max() <= 5e-6
+        assert np.abs(so.joints[f, :24].numpy() - j64).max() <= 5e-6

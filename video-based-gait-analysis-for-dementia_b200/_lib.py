@@ -36,6 +36,8 @@ _SIGS = {
     "gait_linear": [P, I64, P, I64, P, P, I64, P, I64, I64, I64, I64, P],
     "gait_prepare_weight": [P, P, I64, P],
     "gait_release_weight": [P],
+    "gait_split_weight": [P, P, I64, P],
+    "gait_linear_prepared": [P, I64, P, I64, P, I64, P, P, P, I64, P, I64, I64, I64, I64, P],
     "gait_debug_linear_trace": [P],
     "gait_debug_gru_trace": [P],
     "gait_gru_workspace_bytes": [I64, I64, I64],
@@ -127,37 +129,59 @@ def call(name: str, *args):
         raise GaitLibraryError(f"{name} failed ({rc}: {kind}): {detail}")
 
 
-_prepared = {}      # data_ptr of a registered weight -> (weakref to its owner, lo tensor, version)
+_prepared = {}      # data_ptr of a registered weight -> (weakref to its owner, [hi|lo] tensor, version)
+_owner_key = {}     # id(owner tensor) -> data_ptr it was registered under (an owner whose storage moved drops its old entry)
 
 
 def _drop_prepared(key):
     ent = _prepared.pop(key, None)
-    if ent is not None and _lib is not None:
-        try:
-            _lib.gait_release_weight(key)
-        except Exception:  # noqa: BLE001  (interpreter shutdown)
-            pass
+    if ent is not None:
+        for oid, k in list(_owner_key.items()):
+            if k == key:
+                _owner_key.pop(oid, None)
+        if _lib is not None:
+            try:
+                _lib.gait_release_weight(key)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+
+
+def purge_prepared():
+    """Drop every registered weight whose owner is gone or no longer lives at the registered address (a Parameter keeps its
+    identity through module.to(device) / `.data = ...` / load_state_dict(assign=True) while its storage changes, and the
+    caching allocator may hand the old range to another tensor)."""
+    for key, (ref, _lo, _ver) in list(_prepared.items()):
+        w = ref()
+        if w is None or w.data_ptr() != key:
+            _drop_prepared(key)
 
 
 def prepare_weight(w: torch.Tensor) -> torch.Tensor:
     """Register the constant FP32 CUDA weight `w` (contiguous; a Parameter, buffer or packed tensor that its owner keeps
-    alive) with the library: its TF32 lo part is computed once and the GEMMs that use `w` (or a view into it) load it by TMA
-    instead of recomputing it per call.  Idempotent; re-prepared when `w` was modified in place; released when `w` is
-    garbage-collected."""
+    alive) with the library: its TF32 hi/lo split is computed once and the GEMMs that use `w` (or a view into it) load it by
+    TMA instead of recomputing it per call.  Idempotent; re-prepared when `w` was modified in place; released when `w` is
+    garbage-collected, when it is registered again after its storage moved, or by purge_prepared() (modules call it from
+    _apply, i.e. on .to() / .cuda() / .float())."""
     import weakref
     if not (torch.is_tensor(w) and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
         raise GaitLibraryError("prepare_weight: expected a contiguous float32 CUDA tensor")
     key = w.data_ptr()
+    old = _owner_key.get(id(w))
+    if old is not None and old != key:
+        _drop_prepared(old)                       # same tensor object, new storage: the old range is no longer ours
     hit = _prepared.get(key)
     if hit is not None and hit[0]() is w and hit[2] == w._version:
         return w
     if hit is not None:
-        _drop_prepared(key)
+        _drop_prepared(key)                       # another (dead or moved) owner had this address, or w changed in place
     if w.numel() % 4:
         return w                                  # not TMA-addressable anyway
-    lo = torch.empty((2,) + tuple(w.shape), device=w.device, dtype=torch.float32)    # [hi | lo]
-    call("gait_prepare_weight", key, ptr(lo), w.numel(), stream_ptr())
-    _prepared[key] = (weakref.ref(w, lambda _r, k=key: _drop_prepared(k)), lo, w._version)
+    with torch.cuda.device(w.device):
+        lo = torch.empty((2,) + tuple(w.shape), device=w.device, dtype=torch.float32)    # [hi | lo]
+        call("gait_prepare_weight", key, ptr(lo), w.numel(), stream_ptr())
+    oid = id(w)
+    _prepared[key] = (weakref.ref(w, lambda _r, k=key, o=oid: (_owner_key.pop(o, None), _drop_prepared(k))), lo, w._version)
+    _owner_key[oid] = key
     return w
 
 

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "gaitb200.h"
 
 namespace gait {
@@ -53,6 +55,19 @@ inline int check_launch(const char* what) {
         if (rc__ != GAIT_OK) return rc__; \
     } while (0)
 
+// Per-device caches (a process may drive several GPUs, e.g. module.to('cuda:1') or one thread per device): SM count, and a
+// once-per-device guard for cudaFuncSetAttribute (the attribute applies to the current device only).
+int device_sm_count();                                   // api.cu
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    // true exactly until mark() was called for the current device
+    bool needed(int* dev) const {
+        cudaGetDevice(dev);
+        return *dev >= 64 || !((done.load(std::memory_order_acquire) >> *dev) & 1ull);
+    }
+    void mark(int dev) { if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release); }
+};
+
 // internal (not exported) variants used by composite entry points
 int linear_launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
@@ -67,6 +82,12 @@ int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, c
                      int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int splits,
                      int64_t split_stride, cudaStream_t stream);
 int linear_path();
+// prepared (pre-split) weight lookup of the tensor-core GEMM; an explicit operand set with PreparedOverride wins over the registry
+struct PreparedOverride {
+    const float* prev_w; const float* prev_hilo; int64_t prev_n;
+    PreparedOverride(const float* W, const float* hilo, int64_t n);
+    ~PreparedOverride();
+};
 // Call-site knob of the tensor-core GEMM: k-blocks (32 k) accumulated in tensor memory between promotions to FP32 registers
 // (0 = by K: 1 for K >= 512, else 2).  1 is the more accurate, 2 the faster setting (see linear_tc.cu).
 extern thread_local int g_linear_promote_kb;
@@ -81,6 +102,8 @@ int make_tensor_map_2d(void* map, int elem_bytes, const void* ptr, uint64_t dim0
 
 int make_tensor_map_3d_f32(void* map, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
                            uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, bool swizzle128);
+// internal return code of gru_recurrent_launch: the launch was refused, run the per-step path instead
+constexpr int GAIT_GRU_RETRY_PER_STEP = 1;
 // gru_rec.cu: the whole recurrence of one GRU layer/direction in one persistent cluster kernel
 bool gru_recurrent_eligible(const float* gi, const float* W_hh, const float* h0, const float* y, int64_t ldy,
                             const float* resid, int64_t ldres, const float* out, int64_t ldout, int64_t S, int64_t T,

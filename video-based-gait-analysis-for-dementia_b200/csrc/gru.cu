@@ -109,25 +109,31 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
         // up to 192 sequences run as consecutive 64-sequence launches of the persistent kernel (beyond that the per-step
         // GEMMs, whose efficiency grows with the number of rows, win; measured with scripts/stage_sweep.py)
         constexpr int64_t kChunk = 64;
-        static int64_t kMaxChunked = -1;              // GAITB200_GRU_MAXCHUNKED: A/B switch for the crossover (scripts/gru_s_sweep.py)
+        // crossover measured on B200 (scripts/gru_s_sweep.py, profiles/r02a_gru_s_sweep.md): GRU stage M frames/s at
+        // S = 64/128/192/256/512/1024: chunks 2.22/2.31/2.41/2.39/2.36/2.32, per-step 1.92/2.34/1.84/2.20/2.94/3.38
+        static int64_t kMaxChunked = -1;              // GAITB200_GRU_MAXCHUNKED: A/B switch for the crossover
         if (kMaxChunked < 0) {
             const char* e = getenv("GAITB200_GRU_MAXCHUNKED");
-            kMaxChunked = e ? atoll(e) : 192;
+            kMaxChunked = e ? atoll(e) : 320;
         }
         const int64_t S0 = std::min<int64_t>(S, kChunk);
         if (S <= kMaxChunked && gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S0, T, H)) {
             unsigned int* counter = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);
             uintptr_t lo_addr = (reinterpret_cast<uintptr_t>(counter) + 128 * (size_t)(H / 16 + 1) + 127) & ~(uintptr_t)127;
-            for (int64_t s0 = 0; s0 < S; s0 += kChunk) {
+            bool refused = false;
+            for (int64_t s0 = 0; s0 < S && !refused; s0 += kChunk) {
                 const int64_t Sc = std::min<int64_t>(kChunk, S - s0);
-                GAIT_TRY(gru_recurrent_launch(gi + s0 * T * 3 * H, W_hh, b_hh, h0 ? h0 + s0 * H : nullptr, y + s0 * T * ldy, ldy,
-                                              resid ? resid + s0 * T * ldres : nullptr, ldres, out ? out + s0 * T * ldout : nullptr,
-                                              ldout, hn ? hn + s0 * H : nullptr, Sc, T, H, reverse, counter,
-                                              reinterpret_cast<float*>(lo_addr), st));
+                const int rc = gru_recurrent_launch(gi + s0 * T * 3 * H, W_hh, b_hh, h0 ? h0 + s0 * H : nullptr, y + s0 * T * ldy, ldy,
+                                                    resid ? resid + s0 * T * ldres : nullptr, ldres, out ? out + s0 * T * ldout : nullptr,
+                                                    ldout, hn ? hn + s0 * H : nullptr, Sc, T, H, reverse, counter,
+                                                    reinterpret_cast<float*>(lo_addr), st);
+                if (rc == GAIT_GRU_RETRY_PER_STEP) refused = true;      // no co-residency guarantee: per-step path below
+                else if (rc != GAIT_OK) return rc;
             }
-            return GAIT_OK;
+            if (!refused) return GAIT_OK;
+            if (gru_path == 2) return GAIT_ERR_CUDA;                    // set_error was filled by the launcher
         }
-        if (gru_path == 2) {
+        else if (gru_path == 2) {
             set_error("gru_layer: persistent recurrent kernel not eligible for S=%lld T=%lld H=%lld", (long long)S, (long long)T, (long long)H);
             return GAIT_ERR_UNSUPPORTED;
         }

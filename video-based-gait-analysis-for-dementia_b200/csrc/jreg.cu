@@ -130,8 +130,14 @@ joint_regress_stream_kernel(const float* __restrict__ verts, const float* __rest
     for (int it = 0; it < nst; ++it) {
         const int slot = it % D;
         asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");      // this thread's copies of stage `it` have landed
+#ifdef GAIT_JREG_EXP_NOLOAD
+        if (it < D - 1)
+#endif
         mbar_wait(bar0 + 8u * slot, (it / D) & 1);                            // ... and the weights
         __syncthreads();                                                      // everyone's copies; everyone is done with stage it-1
+#ifdef GAIT_JREG_EXP_NOLOAD      // timing experiment only (wrong results): no vertex / weight traffic after the prologue
+        if (false)
+#endif
         if (it + D - 1 < nst) issue(it + D - 1);                              // refills the slot of stage it-1
         asm volatile("cp.async.commit_group;" ::: "memory");
         const float* sX = reinterpret_cast<const float*>(smem + slot * C::STAGE) + lane * XPITCH;
@@ -143,8 +149,13 @@ joint_regress_stream_kernel(const float* __restrict__ verts, const float* __rest
             const float4 x1 = *reinterpret_cast<const float4*>(sX + gi * 12 + 4);
             const float4 x2 = *reinterpret_cast<const float4*>(sX + gi * 12 + 8);
             // vertices: (x0.x x0.y x0.z) (x0.w x1.x x1.y) (x1.z x1.w x2.x) (x2.y x2.z x2.w)
+#ifdef GAIT_JREG_EXP_ROWS        // timing experiment only (wrong results): FMAs for the first rows only
+            constexpr int JN = GAIT_JREG_EXP_ROWS;
+#else
+            constexpr int JN = JT;
+#endif
 #pragma unroll
-            for (int j = 0; j < JT; ++j) {
+            for (int j = 0; j < JN; ++j) {
                 const float4 w = sW[gi * JT + j];                             // warp-uniform address: broadcast
                 acc[j][0] = fmaf(w.x, x0.x, fmaf(w.y, x0.w, fmaf(w.z, x1.z, fmaf(w.w, x2.y, acc[j][0]))));
                 acc[j][1] = fmaf(w.x, x0.y, fmaf(w.y, x1.x, fmaf(w.z, x1.w, fmaf(w.w, x2.z, acc[j][1]))));
@@ -190,7 +201,12 @@ inline int64_t groups_per_cta(int64_t V) { return ceil_div(ceil_div(ceil_div(V, 
 template <int JT>
 static int launch(const float* verts, const float* packed, float* out, int64_t F, int64_t V, int Rj, cudaStream_t stream) {
     using C = Cfg<JT>;
-    GAIT_CUDA(cudaFuncSetAttribute(joint_regress_stream_kernel<JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    static PerDeviceOnce attr_once;
+    int dev = 0;
+    if (attr_once.needed(&dev)) {
+        GAIT_CUDA(cudaFuncSetAttribute(joint_regress_stream_kernel<JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_once.mark(dev);
+    }
     const int64_t gpc = groups_per_cta(V);
     const int blocks = (int)ceil_div(Rj, JT);
     for (int rb = 0; rb < blocks; ++rb) {

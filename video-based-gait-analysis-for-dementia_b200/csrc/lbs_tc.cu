@@ -49,14 +49,22 @@ __device__ __forceinline__ float rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+// Bounded spin: a protocol bug becomes a launch failure (trap) after ~4 s instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
+    uint32_t ok, spins = 0;
+    unsigned long long t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: a waiting warp sleeps instead of taking issue slots
+        if (!ok && (++spins & 0x3FFu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -123,7 +131,7 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
 // consumer group has stored the skinned vertices.  With ONE ring of 6 combined stages only ~3 HBM loads were in flight per
 // SM (the other 3 slots being processed by the 3 consumer groups): the kernel sat at 4.0-4.7 TB/s with nothing saturated.
 #ifndef GAIT_LBS_NA
-#define GAIT_LBS_NA 3
+#define GAIT_LBS_NA 4
 #endif
 #ifndef GAIT_LBS_NV
 #define GAIT_LBS_NV 6
@@ -132,7 +140,12 @@ constexpr int NA = GAIT_LBS_NA;                          // transform-blob stage
 constexpr int NV = GAIT_LBS_NV;                          // v_posed stages (HBM latency); a slot is released as soon as its rows are in registers
 constexpr int NACC = 4;                                  // TMEM accumulator buffers (4 x 96 = 384 columns)
 constexpr int NG = 3;                                    // consumer groups
+#ifndef GAIT_LBS_NMMA
+#define GAIT_LBS_NMMA 2
+#endif
+constexpr int NMMA = GAIT_LBS_NMMA;                      // MMA-issuing warps, items dealt round-robin
 static_assert(NV % NG == 0, "a consumer group must meet every phase of the v_posed barriers it waits on");
+static_assert(NA % NMMA == 0 && NACC % NMMA == 0, "an MMA warp must meet every phase of the blob / accumulator barriers it waits on");
 constexpr int V_STAGE = FT * V_ROW;                      // 12 288 B
 constexpr int OFF_A = 0;
 constexpr int OFF_V = OFF_A + NA * A_BLOB;
@@ -147,6 +160,7 @@ constexpr int NCOMPUTE = NG * 128;
 constexpr int W_PROD_A = NCOMPUTE / 32;                  // warp roles after the consumer warps
 constexpr int W_MMA = NCOMPUTE / 32 + 1;
 constexpr int W_PROD_V = NCOMPUTE / 32 + 2;
+constexpr int W_MMA2 = NCOMPUTE / 32 + 3;                // second MMA issuer (NMMA == 2)
 constexpr int W_LOADER = NCOMPUTE / 32 + 4;              // 4 warps (aligned to a warpgroup: TMEM lane quarter = warp & 3)
 constexpr int THREADS3 = NCOMPUTE + 128 + 128;           // + {A producer, MMA, V producer, idle} + weight-loader warpgroup
 
@@ -246,7 +260,7 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
         }
         for (int b = 0; b < 2; ++b) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(WFULL(b)) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WFREE(b)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(WFREE(b)), "r"(NMMA) : "memory");   // one commit per MMA warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -329,8 +343,13 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(WFULL(b));
         }
-    } else if (warp == W_MMA) {
-        // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
+    } else if (warp == W_MMA || (NMMA == 2 && warp == W_MMA2)) {
+        // ---------------------------------------------------------------- MMA issuers (warp-uniform loop, one lane issues)
+        // The loop body of an issuing warp is a serial latency chain (barrier probes -> fence -> 9 MMAs -> commits, ~1500
+        // cycles): with ONE issuer it bounded the whole kernel - removing every load (A blobs and v_posed) changed nothing
+        // (36 vs 41 us at 1024 frames).  Two warps therefore take alternate items; both walk all items so that each sees
+        // every weight-tile change, and each commits the tile's WFREE after its own last MMA of the tile.
+        const int mpar = (warp == W_MMA) ? 0 : 1;
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
         constexpr uint32_t A_LBO = NCOL * 16, SBO = 128;
         int cur_tile = -1, widx = -1;
@@ -344,6 +363,17 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                 mbar_wait(WFULL(widx & 1), (widx >> 1) & 1);
                 cur_tile = tile;
             }
+            ItemCursor nx = c;
+            nx.next();
+            const bool last_of_tile = (n + 1 == n_total) || nx.tile != tile;
+            if ((n % NMMA) != mpar) {
+                // the other warp's item; at the end of a tile this warp still signals that ITS MMAs on the tile have retired
+                if (last_of_tile && elect_one())
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(WFREE(widx & 1)) : "memory");
+                __syncwarp();
+                c = nx;
+                continue;
+            }
             const int a = n % NACC;
             if (n >= NACC) mbar_wait(ACCFREE(a), ((n / NACC) - 1) & 1);
             mbar_wait(FULL_A(s), (n / NA) & 1);
@@ -351,9 +381,6 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             const uint32_t a_hi = smem_u32(smem + OFF_A + s * A_BLOB), a_lo = a_hi + A_PART;
             const uint32_t acc = tmem_d + (uint32_t)(a * NCOL);
             const uint32_t w_hi = tmem_d + (uint32_t)(TMEM_W + (widx & 1) * W_COLS), w_lo = w_hi + NJ;
-            ItemCursor nx = c;
-            nx.next();
-            const bool last_of_tile = (n + 1 == n_total) || nx.tile != tile;
             if (elect_one()) {
                 // D[128 x 96] = W(128 x 24, tensor memory) . Aop(96 x 24, shared memory)^T, split-TF32: small cross terms first
 #pragma unroll
@@ -413,6 +440,11 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             }
             const int a = n % NACC;
             mbar_wait(FULL_V(s), ph);                              // v_posed rows visible
+            // A parity wait cannot tell phase k from phase k - 2, and this group meets only every NG-th use of accumulator a.
+            // Use k - 1 (item n - NACC) was issued by the same MMA warp as this one and may not have completed when the group
+            // gets here (its previous item n - NG belongs to the OTHER issuing warp), so that phase is awaited first; use
+            // k - 2 is complete by the in-order argument (same issuing warp as item n - 2 NMMA.. which this group consumed).
+            if (n >= NACC) mbar_wait(MMAD(a), ((n / NACC) - 1) & 1);
             mbar_wait(MMAD(a), (n / NACC) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t t[NCOL];
@@ -559,18 +591,16 @@ static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, co
                  "smpl_lbs_tc: v_posed rows must be padded to 384*ceil(V/128) floats (ldv %% 4 == 0, 16-byte aligned)");
     GAIT_REQUIRE(aligned16(Aop) && aligned16(Wpack), "smpl_lbs_tc: operand blobs must be 16-byte aligned");
     GAIT_REQUIRE(F < (1ll << 31) && V < (1ll << 31) && ceil_div(F, lbs::FT) < 65536, "smpl_lbs_tc: size too large");
-    static bool attr = false;
-    static int n_sms = 0;
-    if (!attr) {
+    static PerDeviceOnce attr_once;
+    int dev = 0;
+    if (attr_once.needed(&dev)) {
         GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
         GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
         GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
         GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
-        int dev = 0;
-        GAIT_CUDA(cudaGetDevice(&dev));
-        GAIT_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr = true;
+        attr_once.mark(dev);
     }
+    const int n_sms = device_sm_count();
     const int64_t groups = ceil_div(F, lbs::FT);
     const int64_t n_items = tiles * groups;
     GAIT_REQUIRE(n_items < (1ll << 31), "smpl_lbs_tc: too many work items");

@@ -527,10 +527,11 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
                   int64_t ldcin, float* C, int64_t ldc, int P_rows, int Q_rows, int K, int transposed, int splits,
                   int64_t split_stride, cudaStream_t stream) {
     using cfg = Cfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;                               // per kernel instantiation and per device
+    int dev = 0;
+    if (attr_once.needed(&dev)) {
         GAIT_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, QLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM));
-        attr_set = true;
+        attr_once.mark(dev);
     }
     const int nkb = (K + BK - 1) / BK;
     const int kb_per_split = (nkb + splits - 1) / splits;
@@ -541,12 +542,7 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
     }
     const int tiles_p = (int)ceil_div(P_rows, BM), tiles_q = (int)ceil_div(Q_rows, BN);
     const int n_items = tiles_p * tiles_q * splits;
-    static int n_sms = 0;
-    if (n_sms == 0) {
-        int dev = 0;
-        GAIT_CUDA(cudaGetDevice(&dev));
-        GAIT_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int n_sms = device_sm_count();
     // persistent CTAs, one per SM; balance the number of items per CTA
     const int per_cta = (int)ceil_div(n_items, n_sms);
     dim3 grid((unsigned)ceil_div(n_items, per_cta));
@@ -596,10 +592,24 @@ namespace {
 struct PreparedWeight { const float* base; const float* hilo; int64_t n; };     // hilo: [RN hi (n) | lo (n)]
 std::mutex g_prep_mutex;
 std::vector<PreparedWeight> g_prepared;
+thread_local PreparedWeight g_override = {nullptr, nullptr, 0};          // explicit operand of gait_linear_prepared
 }  // namespace
+
+PreparedOverride::PreparedOverride(const float* W, const float* hilo, int64_t n)
+    : prev_w(g_override.base), prev_hilo(g_override.hilo), prev_n(g_override.n) { g_override = {W, hilo, n}; }
+PreparedOverride::~PreparedOverride() { g_override = {prev_w, prev_hilo, prev_n}; }
 
 // prepared hi / lo pointers matching W (which may point inside a registered array); false when W is not prepared
 static bool find_prepared(const float* W, int64_t n_needed, const float** hi, const float** lo) {
+    if (g_override.base) {                                // explicit handle: no global lookup at all
+        const auto& e = g_override;
+        if (W >= e.base && W + n_needed <= e.base + e.n) {
+            *hi = e.hilo + (W - e.base);
+            *lo = e.hilo + e.n + (W - e.base);
+            return true;
+        }
+        return false;
+    }
     std::lock_guard<std::mutex> lock(g_prep_mutex);
     for (const auto& e : g_prepared)
         if (W >= e.base && W + n_needed <= e.base + e.n) {
@@ -667,6 +677,23 @@ int gait_prepare_weight(const float* W, float* W_hilo, int64_t n, gait_stream_t 
         if (e.base == W) { e.hilo = W_lo; e.n = n; return GAIT_OK; }
     gait::g_prepared.push_back({W, W_lo, n});
     return GAIT_OK;
+}
+
+int gait_split_weight(const float* W, float* W_hilo, int64_t n, gait_stream_t stream) {
+    GAIT_REQUIRE(n >= 0 && (n == 0 || (W && W_hilo)), "split_weight: null pointer or negative size");
+    GAIT_REQUIRE((n & 3) == 0 && gait::aligned16(W_hilo), "split_weight: n must be a multiple of 4 and the split buffer 16-byte aligned");
+    if (n == 0) return GAIT_OK;
+    gait::split_hilo_kernel<<<(unsigned)gait::ceil_div(n, 256), 256, 0, gait::as_stream(stream)>>>(W, W_hilo, n);
+    return gait::check_launch("split_weight");
+}
+
+int gait_linear_prepared(const float* A, int64_t lda, const float* W, int64_t ldw, const float* W_hilo, int64_t n_prepared,
+                         const float* W_base, const float* bias, const float* Cin, int64_t ldcin, float* C, int64_t ldc,
+                         int64_t M, int64_t N, int64_t K, gait_stream_t stream) {
+    GAIT_REQUIRE(W_hilo && W_base && n_prepared > 0 && gait::aligned16(W_hilo), "linear_prepared: prepared operand missing or misaligned");
+    GAIT_REQUIRE(W >= W_base && W + ((N > 0 ? N - 1 : 0) * ldw + K) <= W_base + n_prepared, "linear_prepared: W lies outside the prepared array");
+    gait::PreparedOverride scope(W_base, W_hilo, n_prepared);
+    return gait::linear_launch(A, lda, W, ldw, bias, Cin, ldcin, C, ldc, M, N, K, gait::as_stream(stream));
 }
 
 int gait_release_weight(const float* W) {

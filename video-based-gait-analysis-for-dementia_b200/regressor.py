@@ -89,7 +89,9 @@ class Regressor(nn.Module):
     def _apply(self, fn, *a, **k):
         self._packed = None
         self._folded = {}
-        return super()._apply(fn, *a, **k)
+        r = super()._apply(fn, *a, **k)
+        L.purge_prepared()                       # prepared-weight entries of tensors that moved (.to / .cuda / .float)
+        return r
 
     def fold(self, n_iter=3):
         """Opt-in weight folding.  spin.py:244-265 puts no non-linearity between fc1, fc2 and the decoders, and dropout is the

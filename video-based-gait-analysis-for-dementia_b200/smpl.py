@@ -188,7 +188,9 @@ class SMPL(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._packed = None
-        return super()._apply(fn, *a, **k)
+        r = super()._apply(fn, *a, **k)
+        L.purge_prepared()                       # prepared-weight entries of tensors that moved (.to / .cuda / .float)
+        return r
 
     def _load_from_state_dict(self, *a, **k):
         self._packed = None

@@ -74,6 +74,11 @@ class TemporalEncoder(nn.Module):
         self.use_residual = use_residual
         self.input_size = input_size
 
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        L.purge_prepared()                       # prepared-weight entries of GRU weights that moved (.to / .cuda / .float)
+        return r
+
     @torch.no_grad()
     def forward(self, x):
         """x (N,T,F) -> (N,T,F') : GRU over T, optional relu+Linear, residual when F' == F."""
