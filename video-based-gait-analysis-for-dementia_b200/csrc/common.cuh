@@ -112,4 +112,11 @@ int gru_recurrent_launch(const float* gi, const float* W_hh, const float* b_hh, 
                          const float* resid, int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T,
                          int64_t H, int reverse, unsigned int* counter, float* hlo, cudaStream_t stream);
 
+// gru_small.cu: weight-stationary recurrence for 1-2 sequences (W_hh resident in registers + shared memory for all T steps)
+bool gru_small_eligible(const float* gi, const float* W_hh, const float* h0, const float* y, int64_t ldy, int64_t S, int64_t T,
+                        int64_t H);
+int gru_small_launch(const float* gi, const float* W_hh, const float* b_hh, const float* h0, float* y, int64_t ldy,
+                     const float* resid, int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T, int reverse,
+                     unsigned int* flags, cudaStream_t stream);
+
 }  // namespace gait

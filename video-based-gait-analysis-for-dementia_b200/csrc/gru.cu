@@ -105,6 +105,18 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
         const char* e = getenv("GAITB200_GRU_PATH");
         gru_path = e ? atoi(e) : 0;
     }
+    // one or two sequences (a single long clip, BASELINE configs[3]): weight-stationary kernel, W_hh stays in registers and
+    // shared memory for all T steps (gru_small.cu); GAITB200_GRU_SMALL=0 disables it (A/B)
+    static int gru_small = -1;
+    if (gru_small < 0) {
+        const char* e = getenv("GAITB200_GRU_SMALL");
+        gru_small = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (gru_path != 1 && gru_small && gru_small_eligible(gi, W_hh, h0, y, ldy, S, T, H) && T >= 4) {
+        unsigned int* flags = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);
+        const int rc = gru_small_launch(gi, W_hh, b_hh, h0, y, ldy, resid, ldres, out, ldout, hn, S, T, reverse, flags, st);
+        if (rc != GAIT_GRU_RETRY_PER_STEP) return rc;
+    }
     if (gru_path != 1 && linear_path() != 1) {
         // up to 192 sequences run as consecutive 64-sequence launches of the persistent kernel (beyond that the per-step
         // GEMMs, whose efficiency grows with the number of rows, win; measured with scripts/stage_sweep.py)
