@@ -189,6 +189,7 @@ int gait_smpl_lbs(const float* v_posed, int64_t ldv, const float* A, const float
  *   Wpack  = gait_smpl_lbs_pack(lbs_weights)  (gait_smpl_lbs_pack_bytes(V) bytes, once per model)
  *   Aop    = the pose-chain kernel's tensor operand output
  *   v_posed rows padded: ldv >= 384*ceil(V/128), ldv % 4 == 0 (rows are bulk-copied 1536 B at a time)
+ *   verts (F,V,3) contiguous, 8-byte aligned, V even
  *   jx (V) optional: one joint-regressor row (the MPII thorax row of J_regressor_extra); its dot
  *   product with the skinned vertices is emitted as partial sums over 32-vertex slices,
  *   jx_partial (gait_smpl_lbs_jx_parts(V) = 4*ceil(V/128), F, 3), summed by gait_joints_assemble (extra_parts = that). */

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--backend", default="nccl")
 ap.add_argument("--mode", default="peer-copy")
 ap.add_argument("--chunks", type=int, default=2)
+ap.add_argument("--smpl-chunks", type=int, default=1)
 ap.add_argument("--seqs", type=int, default=10)
 ap.add_argument("--frames", type=int, default=8)
 ap.add_argument("--same-gpu", action="store_true", help="all ranks on cuda:0 (gloo + CUDA IPC on a one-GPU box)")
@@ -44,7 +45,7 @@ S, T = args.seqs, args.frames
 feats = synthetic.make_features(S, T, seed=77)                  # identical on every rank; each takes its block
 lo, hi = shard_bounds(S, world, rank)
 head = make_head()
-rg = RootGather(head, S, T, mode=args.mode, chunks=args.chunks)
+rg = RootGather(head, S, T, mode=args.mode, chunks=args.chunks, smpl_chunks=args.smpl_chunks)
 rg.load_features(feats[lo:hi])
 for _ in range(2):                                               # twice: buffers are reused across steps
     rg.run()
@@ -53,7 +54,7 @@ res = None
 if rank == 0:
     got = {k: v.clone() for k, v in rg.gathered().items()}
     ref = make_head()(feats.cuda())
-    res = {"mode": args.mode, "backend": args.backend, "world": world, "chunks": len(rg.cb),
+    res = {"mode": args.mode, "backend": args.backend, "world": world, "chunks": len(rg.cb), "pieces": len(rg.pieces),
            "root_ingest_bytes": rg.root_ingest_bytes}
     for k, v in got.items():
         res[k + "_max_abs_diff"] = float((v - ref[k]).abs().max())

@@ -40,6 +40,14 @@ def test_two_ranks_one_gpu_ipc_gather_matches_single_process(tmp_path, mode):
     _check(res)
 
 
+def test_two_ranks_one_gpu_smpl_chunks(tmp_path):
+    """One encoder + regressor pass per rank, the SMPL part and the gather in 3 pieces (odd frame count, ragged pieces)."""
+    res = _run(tmp_path, 2, 29634, "--backend", "gloo", "--same-gpu", "--mode", "peer-store", "--chunks", "1", "--smpl-chunks", "3",
+               "--seqs", "9", "--frames", "5")
+    assert res["pieces"] == 3
+    _check(res)
+
+
 def test_two_ranks_one_gpu_joints_only_gather(tmp_path):
     res = _run(tmp_path, 2, 29633, "--backend", "gloo", "--same-gpu", "--mode", "peer-copy", "--chunks", "1", "--seqs", "7",
                "--frames", "16", "--joints-only")
@@ -52,5 +60,5 @@ def test_nccl_ranks_gather_matches_single_process(tmp_path, mode):
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     res = _run(tmp_path, 2, 29640 + ["nccl", "peer-copy", "peer-store"].index(mode), "--backend", "nccl", "--mode", mode, "--chunks", "2",
-               "--seqs", "12", "--frames", "16")
+               "--smpl-chunks", "2", "--seqs", "12", "--frames", "16")
     _check(res)

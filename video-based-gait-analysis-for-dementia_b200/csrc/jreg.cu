@@ -2,11 +2,11 @@
 // lib/models/spin.py:279-282 with the (17,6890) H36M regressor; lib/models/smpl.py:113 with J_regressor_extra) as ONE
 // streaming pass over the mesh: 82 680 B read per frame against 12*Rj B written - an HBM stream.
 //
-// It is also 17 FMA per mesh float, i.e. ~53 % of the nominal FP32 FMA rate at the HBM roofline - and a three-register FFMA
-// issues only every other cycle per scheduler (register-file ports), which puts scalar FMAs ABOVE the roofline time.  The
-// inner loop therefore uses Blackwell's packed fma.rn.f32x2 (two FMAs per instruction): regressor rows are processed in
-// PAIRS - accumulators (row j, row j+1) in one 64-bit register pair, weights packed the same way, the vertex coordinate
-// duplicated into both halves - and it must spend its issue slots on FMAs only:
+// It is also 17 FMA per mesh float, i.e. ~53 % of the nominal FP32 FMA rate at the HBM roofline, so the inner loop must
+// spend its issue slots on FMAs only (measured on B200, scripts/jreg_time.py with the GAIT_JREG_EXP_* builds, 1024 frames:
+// whole kernel 34 us; without vertex loads 31 us; with 1 row of FMAs instead of 17 24 us; with neither 12 us - the FMA
+// phase, not the HBM stream, bounds it.  Row pairs on packed fma.rn.f32x2 were tried: 39 us, the operand duplication and
+// 168 registers cost more than the halved FMA count buys):
 //   * lane = frame.  A warp owns 32 frames, so the regressor weights it multiplies with are warp-uniform: they are read
 //     from shared memory as broadcast 128-bit loads (one wavefront per 4 weights per 32 frames) and every frame's 3*Rj
 //     running sums stay in registers for the whole pass - no cross-lane reduction in the loop.
@@ -60,8 +60,7 @@ __device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
     return v;
 }
 
-// packed (Gpad, JT/2, 4, 2) with packed[g][p][k][h] = Jreg[r0 + 2 p + h][4 g + k], zero outside (rows >= Rj, vertices >= V):
-// one 128-bit shared-memory load yields the weights of a row PAIR for two vertices, already in f32x2 operand order
+// packed (Gpad, JT, 4) with packed[g][j][k] = Jreg[r0 + j][4 g + k], zero outside (rows >= Rj, vertices >= V)
 __global__ void jreg_pack_kernel(const float* __restrict__ Jreg, float* __restrict__ packed, int V, int Rj, int JT, int Gpad,
                                  int blocks) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -69,21 +68,9 @@ __global__ void jreg_pack_kernel(const float* __restrict__ Jreg, float* __restri
     if (i >= per_block * blocks) return;
     const int rb = (int)(i / per_block);
     const int rem = (int)(i % per_block);
-    const int g = rem / (JT * 4), p = (rem / 8) % (JT / 2), k = (rem >> 1) & 3, h = rem & 1;
-    const int r = rb * JT + 2 * p + h, v = 4 * g + k;
+    const int g = rem / (JT * 4), j = (rem / 4) % JT, k = rem & 3;
+    const int r = rb * JT + j, v = 4 * g + k;
     packed[i] = (r < Rj && v < V) ? Jreg[(int64_t)r * V + v] : 0.f;
-}
-
-// d = a * b + c on two packed FP32 lanes (sm_100 FFMA2)
-__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
-    unsigned long long ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-    return d;
 }
 
 template <int JT>
@@ -139,10 +126,9 @@ joint_regress_stream_kernel(const float* __restrict__ verts, const float* __rest
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    constexpr int JP = JT / 2;                                         // row pairs
-    float2 acc[JP][3];                                                 // (row 2p, row 2p+1) x component
+    float acc[JT][3];
 #pragma unroll
-    for (int p = 0; p < JP; ++p) { acc[p][0] = make_float2(0.f, 0.f); acc[p][1] = acc[p][0]; acc[p][2] = acc[p][0]; }
+    for (int j = 0; j < JT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; }
 
     for (int it = 0; it < nst; ++it) {
         const int slot = it % D;
@@ -165,26 +151,18 @@ joint_regress_stream_kernel(const float* __restrict__ verts, const float* __rest
             const float4 x0 = *reinterpret_cast<const float4*>(sX + gi * 12);
             const float4 x1 = *reinterpret_cast<const float4*>(sX + gi * 12 + 4);
             const float4 x2 = *reinterpret_cast<const float4*>(sX + gi * 12 + 8);
-            // vertices: (x0.x x0.y x0.z) (x0.w x1.x x1.y) (x1.z x1.w x2.x) (x2.y x2.z x2.w); each coordinate duplicated into
-            // both halves of a register pair (the two rows of a pair multiply the same vertex)
-            const float xs[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
-            float2 xd[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) xd[i] = make_float2(xs[i], xs[i]);
-#ifdef GAIT_JREG_EXP_ROWS        // timing experiment only (wrong results): FMAs for the first row pairs only
+            // vertices: (x0.x x0.y x0.z) (x0.w x1.x x1.y) (x1.z x1.w x2.x) (x2.y x2.z x2.w)
+#ifdef GAIT_JREG_EXP_ROWS        // timing experiment only (wrong results): FMAs for the first rows only
             constexpr int JN = GAIT_JREG_EXP_ROWS;
 #else
-            constexpr int JN = JP;
+            constexpr int JN = JT;
 #endif
 #pragma unroll
-            for (int p = 0; p < JN; ++p) {
-                const float4 wa = sW[(gi * JP + p) * 2];                      // warp-uniform addresses: broadcast loads
-                const float4 wb = sW[(gi * JP + p) * 2 + 1];                  // wa = vertices 0,1; wb = vertices 2,3 (row pair)
-                const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
-                const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    acc[p][c] = ffma2(w0, xd[c], ffma2(w1, xd[3 + c], ffma2(w2, xd[6 + c], ffma2(w3, xd[9 + c], acc[p][c]))));
+            for (int j = 0; j < JN; ++j) {
+                const float4 w = sW[gi * JT + j];                             // warp-uniform address: broadcast
+                acc[j][0] = fmaf(w.x, x0.x, fmaf(w.y, x0.w, fmaf(w.z, x1.z, fmaf(w.w, x2.y, acc[j][0]))));
+                acc[j][1] = fmaf(w.x, x0.y, fmaf(w.y, x1.x, fmaf(w.z, x1.w, fmaf(w.w, x2.z, acc[j][1]))));
+                acc[j][2] = fmaf(w.x, x0.z, fmaf(w.y, x1.y, fmaf(w.z, x2.x, fmaf(w.w, x2.w, acc[j][2]))));
             }
         }
     }
@@ -195,12 +173,9 @@ joint_regress_stream_kernel(const float* __restrict__ verts, const float* __rest
     float* red = reinterpret_cast<float*>(smem);
     float* part = reinterpret_cast<float*>(smem + C::OFF_PART);
 #pragma unroll
-    for (int p = 0; p < JP; ++p)
+    for (int j = 0; j < JT; ++j)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            red[(warp * JT * 3 + (2 * p) * 3 + c) * 32 + lane] = acc[p][c].x;
-            red[(warp * JT * 3 + (2 * p + 1) * 3 + c) * 32 + lane] = acc[p][c].y;
-        }
+        for (int c = 0; c < 3; ++c) red[(warp * JT * 3 + j * 3 + c) * 32 + lane] = acc[j][c];
     __syncthreads();
     for (int i = tid; i < JT * 3 * 32; i += THREADS) {
         float s = 0.f;
@@ -223,7 +198,7 @@ joint_regress_stream_kernel(const float* __restrict__ verts, const float* __rest
     cluster_sync_all();                                                // nobody leaves while rank 0 may still read its partial
 }
 
-inline int rows_per_pass(int Rj) { return Rj <= 10 ? 10 : 18; }       // even: rows are processed in pairs
+inline int rows_per_pass(int Rj) { return Rj <= 9 ? 9 : 17; }
 inline int64_t groups_per_cta(int64_t V) { return ceil_div(ceil_div(ceil_div(V, 4), CL), GS) * GS; }
 
 template <int JT>
@@ -293,8 +268,8 @@ int gait_joint_regress_packed(const float* verts, const float* packed, float* ou
     GAIT_REQUIRE(aligned8(verts) && (V % 2) == 0 && aligned16(packed),
                  "joint_regress_packed: verts must be 8-byte aligned with an even vertex count, packed 16-byte aligned");
     GAIT_REQUIRE(F < (1ll << 31) - 64 && V < (1ll << 28) && ceil_div(F, jreg::FB) * jreg::CL < (1ll << 31), "joint_regress_packed: size too large");
-    if (jreg::rows_per_pass(Rj) == 10) return jreg::launch<10>(verts, packed, out, F, V, Rj, as_stream(stream));
-    return jreg::launch<18>(verts, packed, out, F, V, Rj, as_stream(stream));
+    if (jreg::rows_per_pass(Rj) == 9) return jreg::launch<9>(verts, packed, out, F, V, Rj, as_stream(stream));
+    return jreg::launch<17>(verts, packed, out, F, V, Rj, as_stream(stream));
 }
 
 }  // extern "C"

@@ -28,24 +28,19 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "lbs_layout.cuh"
 
 namespace gait {
 namespace lbs {
 
 constexpr int NJ = 24;
 constexpr int VT = 128;                    // vertices per CTA (UMMA M)
-constexpr int FT = LBS_TC_FT;                 // frames per work item = 16 (lbs_layout.cuh; the chain kernel writes the blobs)
-constexpr int HF = 4;                      // frames a consumer thread handles at a time (48 accumulator columns in registers)
-constexpr int NCOL = FT * 12;              // UMMA N = 192: a tcgen05.mma has a fixed cost of ~130 cycles on this machine, so with
-                                           // N = 96 (8 frames) the 9 MMAs of an item ran at ~40 % of the tensor rate and their
-                                           // serial issue bounded the kernel (no loads: 36 us, no consumers: 33 us, all: 41 us)
+constexpr int FT = 8;                      // frames per CTA
+constexpr int NCOL = FT * 12;              // UMMA N = 96
 constexpr int KC = NJ / 4;                 // 16-byte K chunks = 6
 constexpr int W_PART = KC * VT * 16;       // 12 288 B (hi or lo)
-constexpr int A_PART = KC * NCOL * 16;     // 18 432 B
+constexpr int A_PART = KC * NCOL * 16;     //  9 216 B
 constexpr int W_BLOB = 2 * W_PART;         // 24 576
-constexpr int A_BLOB = 2 * A_PART;         // 36 864
-static_assert(A_BLOB == LBS_TC_AOP_BLOB_BYTES, "operand blob layout shared with the chain kernel");
+constexpr int A_BLOB = 2 * A_PART;         // 18 432
 constexpr int V_ROW = VT * 3 * 4;          //  1 536 B per frame
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,8 +49,20 @@ __device__ __forceinline__ float rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
-// Bounded spin: a protocol bug becomes a launch failure (trap) after ~3 s instead of a hung GPU; the guard's state lives
-// only inside the retry loop (the first probe usually succeeds), so it costs the callers no registers.
+// Plain wait for the consumer warps (every register counts there).  They cannot hang alone: a stuck consumer stops releasing
+// accumulators and slots, the producer / MMA warps then block in the guarded wait below and trap.
+__device__ __forceinline__ void mbar_wait_raw(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: a waiting warp sleeps instead of taking issue slots
+    } while (!ok);
+}
+// Bounded spin (producer, MMA and weight-loader warps): a protocol bug becomes a launch failure (trap) after ~3 s instead of a
+// hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -144,30 +151,21 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
 // consumer group has stored the skinned vertices.  With ONE ring of 6 combined stages only ~3 HBM loads were in flight per
 // SM (the other 3 slots being processed by the 3 consumer groups): the kernel sat at 4.0-4.7 TB/s with nothing saturated.
 #ifndef GAIT_LBS_NA
-#define GAIT_LBS_NA 2
+#define GAIT_LBS_NA 3
 #endif
 #ifndef GAIT_LBS_NV
 #define GAIT_LBS_NV 6
 #endif
 constexpr int NA = GAIT_LBS_NA;                          // transform-blob stages (L2 latency)
 constexpr int NV = GAIT_LBS_NV;                          // v_posed stages (HBM latency); a slot is released as soon as its rows are in registers
-constexpr int NACC = 2;                                  // TMEM accumulator buffers (2 x 192 = 384 columns)
-constexpr int NMB = 4;                                   // "accumulator ready" barriers, indexed n % 4: a consumer group meets only
-                                                         // every NG-th item, and a parity wait cannot tell phase k from k - 2; with
-                                                         // four barriers the previous phase of item n's barrier belongs to item n - 4,
-                                                         // which has completed when the group has consumed item n - NG (one in-order issuer)
+constexpr int NACC = 4;                                  // TMEM accumulator buffers (4 x 96 = 384 columns)
 constexpr int NG = 3;                                    // consumer groups
-#ifndef GAIT_LBS_MB
-#define GAIT_LBS_MB 1
-#endif
-constexpr int MB = GAIT_LBS_MB;                          // items whose barrier probes / MMAs the issuing warp batches per loop iteration
 static_assert(NV % NG == 0, "a consumer group must meet every phase of the v_posed barriers it waits on");
-static_assert(MB <= NA && MB <= NACC, "a batch of items needs its blobs and accumulators at the same time");
 constexpr int V_STAGE = FT * V_ROW;                      // 12 288 B
 constexpr int OFF_A = 0;
 constexpr int OFF_V = OFF_A + NA * A_BLOB;
 constexpr int OFF_BAR = OFF_V + NV * V_STAGE;
-constexpr int N_BARS = 2 * NA + 2 * NV + NMB + NACC + 4;
+constexpr int N_BARS = 2 * NA + 2 * NV + 2 * NACC + 4;
 constexpr int SMEM3 = OFF_BAR + ((N_BARS * 8 + 8 + 127) / 128) * 128;
 static_assert(SMEM3 <= 232448, "shared memory budget");
 constexpr int TMEM_COLS3 = 512;                          // 384 accumulator columns + 2 x 48 weight columns -> 512
@@ -179,7 +177,6 @@ constexpr int W_MMA = NCOMPUTE / 32 + 1;
 constexpr int W_PROD_V = NCOMPUTE / 32 + 2;
 constexpr int W_LOADER = NCOMPUTE / 32 + 4;              // 4 warps (aligned to a warpgroup: TMEM lane quarter = warp & 3)
 constexpr int THREADS3 = NCOMPUTE + 128 + 128;           // + {A producer, MMA, V producer, idle} + weight-loader warpgroup
-constexpr int REGS_CONSUMER = 120, REGS_OTHER = 56;      // setmaxnreg: 384 x 120 + 256 x 56 <= 640 x 96
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -190,14 +187,6 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
 // one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
@@ -212,10 +201,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // Work-item order.  Items are walked tile-major inside super-blocks of GB frame groups: (super-block, vertex tile, group).
 // A CTA's contiguous item range then stays inside one vertex tile for ~47 items (the tile's weights are loaded into tensor
-// memory once), and the transform blobs of a super-block (9.4 MB per 4096 frames) stay L2-resident while the 54 tiles sweep
+// memory once), and the transform blobs of a super-block (GB x 18 KB = 9.4 MB) stay L2-resident while the 54 tiles sweep
 // over them; with one block spanning all frames the 37.7 MB of blobs of a 16 384-frame launch were evicted by the
 // v_posed / verts streams between sweeps (4.7 -> 4.1 TB/s).  Up to GB groups (4096 frames) the order is plain tile-major.
-constexpr int GB = 4096 / LBS_TC_FT;
+constexpr int GB = 512;
 struct ItemCursor {
     int tile, g, g_begin, g_end, tiles, groups;
     __device__ __forceinline__ void init(int item, int tiles_, int groups_) {
@@ -257,10 +246,10 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     auto EMPTY_A = [&](int s) { return bar0 + 8u * (NA + s); };     // the MMAs that read it have retired
     auto FULL_V = [&](int s) { return bar0 + 8u * (2 * NA + s); };  // v_posed rows landed (tx count)
     auto EMPTY_V = [&](int s) { return bar0 + 8u * (2 * NA + NV + s); };     // consumer group done with the slot
-    auto MMAD = [&](int m) { return bar0 + 8u * (2 * NA + 2 * NV + m); };    // the accumulator of item n (m = n % NMB) is ready
-    auto ACCFREE = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NV + NMB + a); };   // accumulator a has been read out
-    auto WFULL = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NV + NMB + NACC + b); };     // weight tile b is in tensor memory
-    auto WFREE = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NV + NMB + NACC + 2 + b); }; // the MMAs that read weight buffer b have retired
+    auto MMAD = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NV + a); };    // accumulator a ready
+    auto ACCFREE = [&](int a) { return bar0 + 8u * (2 * NA + 2 * NV + NACC + a); };   // accumulator a has been read out
+    auto WFULL = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NV + 2 * NACC + b); };     // weight tile b is in tensor memory
+    auto WFREE = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NV + 2 * NACC + 2 + b); }; // the MMAs that read weight buffer b have retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 8 * N_BARS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -279,11 +268,13 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(FULL_V(s)) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(EMPTY_V(s)), "r"(4) : "memory");  // one arrival per consumer warp
         }
-        for (int m = 0; m < NMB; ++m) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(m)) : "memory");
-        for (int a = 0; a < NACC; ++a) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ACCFREE(a)), "r"(4) : "memory");
+        for (int a = 0; a < NACC; ++a) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(MMAD(a)) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ACCFREE(a)), "r"(4) : "memory");
+        }
         for (int b = 0; b < 2; ++b) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(WFULL(b)) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(WFREE(b)), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WFREE(b)) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -296,11 +287,7 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    // register budget (640 threads launch with 96 each): the consumer warpgroups hold 96 accumulator columns + 24 vertex
-    // values + 24 results per thread, the producer / MMA / loader warpgroups need almost nothing
-    // (issued at the top of every role branch: the allocator honours the new limit only inside the region the instruction dominates)
     if (warp == W_PROD_A) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
         // ---------------------------------------------------------------- transform-blob producer (one elected lane)
         ItemCursor c = cur0;
         for (int n = 0; n < item_hi - item_lo; ++n, c.next()) {
@@ -318,7 +305,6 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             __syncwarp();
         }
     } else if (warp == W_PROD_V) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
         // ---------------------------------------------------------------- v_posed producer: runs up to NV items ahead
         ItemCursor c = cur0;
         for (int n = 0; n < item_hi - item_lo; ++n, c.next()) {
@@ -340,7 +326,6 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             __syncwarp();
         }
     } else if (warp >= W_LOADER) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
         // ---------------------------------------------------------------- weight loader: vertex tile -> tensor memory
         // The skinning weights are the M-side operand of every MMA of a vertex tile (~46 work items per CTA), so
         // they live in tensor memory (lane = vertex, columns [hi 24 | lo 24]) instead of being re-read from shared
@@ -358,9 +343,9 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             const float* blob = Wpack + (int64_t)tile * (W_BLOB / 4);
             const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(TMEM_W + b * W_COLS);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
+#pragma unroll
             for (int part = 0; part < 2; ++part) {
-#pragma unroll 1
+#pragma unroll
                 for (int c = 0; c < NJ / 8; ++c) {
                     float v[8];
 #pragma unroll
@@ -373,81 +358,64 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             mbar_arrive(WFULL(b));
         }
     } else if (warp == W_MMA) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));
         // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
-        // The loop body of the issuing warp is a serial latency chain (barrier probes -> fence -> MMAs -> commits): with one
-        // item per iteration it bounded the whole kernel - removing every load (A blobs and v_posed) changed nothing (36 vs
-        // 41 us at 1024 frames).  The probes of MB consecutive items are therefore batched in front of their 9 * MB MMAs, so
-        // the chain is paid once per MB items.  A single issuing thread keeps all MMAs in item order, which the consumers'
-        // parity waits rely on (two issuing warps on alternate items let a consumer group run one accumulator phase ahead of
-        // a lagging issuer: intermittent wrong results, then deadlock - measured).
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(VT >> 4) << 24);
         constexpr uint32_t A_LBO = NCOL * 16, SBO = 128;
         int cur_tile = -1, widx = -1;
         ItemCursor c = cur0;
         const int n_total = item_hi - item_lo;
-        for (int n0 = 0; n0 < n_total; n0 += MB) {
-            const int nb = min(MB, n_total - n0);
-            int wsel[MB];
-            bool last[MB];
-            // probes first: weight tiles, accumulators, transform blobs of the nb items
-#pragma unroll
-            for (int i = 0; i < MB; ++i) {
-                if (i < nb) {
-                    const int n = n0 + i;
-                    if (c.tile != cur_tile) {
-                        ++widx;
-                        mbar_wait(WFULL(widx & 1), (widx >> 1) & 1);
-                        cur_tile = c.tile;
-                    }
-                    wsel[i] = widx & 1;
-                    ItemCursor nx = c;
-                    nx.next();
-                    last[i] = (n + 1 == n_total) || nx.tile != c.tile;
-                    c = nx;
-                    if (n >= NACC) mbar_wait(ACCFREE(n % NACC), ((n / NACC) - 1) & 1);
-                    mbar_wait(FULL_A(n % NA), (n / NA) & 1);
-                }
+        for (int n = 0; n < n_total; ++n) {
+            const int s = n % NA;
+            const int tile = c.tile;
+            if (tile != cur_tile) {
+                ++widx;
+                mbar_wait(WFULL(widx & 1), (widx >> 1) & 1);
+                cur_tile = tile;
             }
+            const int a = n % NACC;
+            if (n >= NACC) mbar_wait(ACCFREE(a), ((n / NACC) - 1) & 1);
+            mbar_wait(FULL_A(s), (n / NA) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(smem + OFF_A + s * A_BLOB), a_lo = a_hi + A_PART;
+            const uint32_t acc = tmem_d + (uint32_t)(a * NCOL);
+            const uint32_t w_hi = tmem_d + (uint32_t)(TMEM_W + (widx & 1) * W_COLS), w_lo = w_hi + NJ;
+            ItemCursor nx = c;
+            nx.next();
+            const bool last_of_tile = (n + 1 == n_total) || nx.tile != tile;
             if (elect_one()) {
+                // D[128 x 96] = W(128 x 24, tensor memory) . Aop(96 x 24, shared memory)^T, split-TF32: small cross terms first
 #pragma unroll
-                for (int i = 0; i < MB; ++i) {
-                    if (i < nb) {
-                        const int n = n0 + i, s = n % NA, a = n % NACC;
-                        const uint32_t a_hi = smem_u32(smem + OFF_A + s * A_BLOB), a_lo = a_hi + A_PART;
-                        const uint32_t acc = tmem_d + (uint32_t)(a * NCOL);
-                        const uint32_t w_hi = tmem_d + (uint32_t)(TMEM_W + wsel[i] * W_COLS), w_lo = w_hi + NJ;
-                        // D[128 x 96] = W(128 x 24, tensor memory) . Aop(96 x 24, shared memory)^T, split-TF32: small cross terms first
+                for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-#pragma unroll
-                            for (int ks = 0; ks < NJ / 8; ++ks) {
-                                const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 8 * ks;
-                                const uint32_t ao = (pass == 1 ? a_lo : a_hi) + 2 * ks * A_LBO;
-                                umma_tf32_ts(acc, wo, make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
-                            }
-                        }
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(n % NMB)) : "memory");
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(EMPTY_A(s)) : "memory");
-                        if (last[i])
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(WFREE(wsel[i])) : "memory");
+                    for (int ks = 0; ks < NJ / 8; ++ks) {
+                        const uint32_t wo = (pass == 0 ? w_lo : w_hi) + 8 * ks;
+                        const uint32_t ao = (pass == 1 ? a_lo : a_hi) + 2 * ks * A_LBO;
+                        umma_tf32_ts(acc, wo, make_desc(ao, A_LBO, SBO), idesc, (pass | ks) ? 1u : 0u);
                     }
                 }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(MMAD(a)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(EMPTY_A(s)) : "memory");
+                if (last_of_tile)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(WFREE(widx & 1)) : "memory");
             }
             __syncwarp();
+            c = nx;
         }
-    } else if (warp == W_MMA + 2) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_OTHER));      // idle warp of the role warpgroup
     } else if (warp < NCOMPUTE / 32) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
         // ---------------------------------------------------------------- consumer groups
         // Thread = vertex (TMEM lane).  Everything an item needs is pulled into registers at once - the 96 accumulator
         // columns (T for 8 frames) and the vertex's 8 v_posed entries - after which the accumulator and the v_posed slot
         // are released immediately; the skinned vertex is stored straight from registers (three 4-byte stores per frame,
         // a warp covering 384 contiguous bytes: the sectors are completed in L2).  The earlier version staged the result
         // in shared memory for 8-byte stores and read it back for the regressor row: ~430 instead of ~220 warp
-        // instructions per item in a kernel that is bound by its instruction-issue latency chain, not by bytes.
+        // instructions per item.  What bounds the kernel (measured, scripts/lbs_sweep.py with the GAIT_LBS_EXP_* builds, 1024
+        // frames): all loads removed 36 us, consumers removed 33 us, complete 41 us - neither the HBM streams nor the
+        // instruction count, but the MMA -> tensor-memory -> register chain: K = 24 in split TF32 is 9 accumulating
+        // MMAs of depth 8, each reading and writing the whole 128 x 96 accumulator (0.9 MB of tensor-memory traffic per
+        // 24 KB of mesh), against which the consumers' tcgen05.ld compete.  Tried and measured slower or equal: v_posed
+        // ring of 9 / 12 slots, two MMA-issuing warps (breaks the in-order argument of the parity waits), 16-frame items
+        // with N = 192 (MMA side 33 -> 27 us, consumer side slower), TMA tensor stores (box starts must be 16-byte
+        // aligned: impossible for odd frames of a (F, 6890, 3) array, scripts/microbench/tma_store.cu).
         const int grp = warp >> 2, quad = warp & 3;                // group, TMEM lane quarter
         const int gt = tid & 127;                                  // thread within the group = vertex within the tile
         int cur_tile = -1;
@@ -479,108 +447,98 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                 }
             }
             const int a = n % NACC;
-            mbar_wait(FULL_V(s), ph);                              // v_posed rows visible
-            // (a parity wait cannot tell phase k from phase k - 2; this group meets only every NG-th item, but all MMAs are
-            // issued by ONE thread in item order and this group has consumed item n - NG, so the previous phase of this
-            // barrier - item n - NMB - has completed: the barrier is in phase k or beyond k)
-            mbar_wait(MMAD(n % NMB), (n / NMB) & 1);
+            mbar_wait_raw(FULL_V(s), ph);                          // v_posed rows visible
+            mbar_wait_raw(MMAD(a), (n / NACC) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#ifdef GAIT_LBS_EXP_NOCONSUME     // timing experiment only (wrong results): consumers release the item without touching it
+            uint32_t t[NCOL];
+            const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * NCOL);
+            tmem_ld32_nowait(taddr, t);
+            tmem_ld32_nowait(taddr + 32, t + 32);
+            tmem_ld32_nowait(taddr + 64, t + 64);
+            float vx[FT], vy[FT], vz[FT];
+            const float* p = sV + gt * 3;
+#pragma unroll
+            for (int f = 0; f < FT; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            // the smem values must have arrived before the slot is handed back to the TMA producer
+            asm volatile("" ::"f"(vx[FT - 1]), "f"(vy[FT - 1]), "f"(vz[FT - 1]) : "memory");
             __syncwarp();
-            if (lane == 0) { mbar_arrive(ACCFREE(a)); mbar_arrive(EMPTY_V(s)); }
+            if (lane == 0) {
+                mbar_arrive(ACCFREE(a));                           // the accumulator can take the MMAs of item n + NACC
+                mbar_arrive(EMPTY_V(s));                           // the slot can take the rows of item n + NV
+            }
+            float ox[FT], oy[FT], oz[FT];
 #pragma unroll
-            for (int k = 0; k < NG; ++k) c.next();
-            continue;
-#endif
-#pragma unroll 1
-            for (int hh = 0; hh < FT / HF; ++hh) {                 // four 4-frame quarters: 48 accumulator columns in registers at a time
-                const int fh = f0 + hh * HF;                       // first frame of this quarter
-                const int nfh = min(HF, F - fh);                   // <= 0: the quarter lies past the last frame
-                uint32_t t[HF * 12];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * NCOL + hh * HF * 12);
-                tmem_ld32_nowait(taddr, t);
-                tmem_ld16_nowait(taddr + 32, t + 32);
-                float vx[HF], vy[HF], vz[HF];
-                const float* p = sV + hh * HF * (VT * 3) + gt * 3;
+            for (int f = 0; f < FT; ++f) {
+                const uint32_t* q = t + f * 12;
+                const float x = vx[f], y = vy[f], z = vz[f];
+                ox[f] = __uint_as_float(q[0]) * x + __uint_as_float(q[1]) * y + __uint_as_float(q[2]) * z + __uint_as_float(q[3]);
+                oy[f] = __uint_as_float(q[4]) * x + __uint_as_float(q[5]) * y + __uint_as_float(q[6]) * z + __uint_as_float(q[7]);
+                oz[f] = __uint_as_float(q[8]) * x + __uint_as_float(q[9]) * y + __uint_as_float(q[10]) * z + __uint_as_float(q[11]);
+            }
+            if (MESH && gt < nv) {
+                float* dst = verts + ((int64_t)f0 * V + v0 + gt) * 3;
 #pragma unroll
-                for (int f = 0; f < HF; ++f) { vx[f] = p[f * (VT * 3)]; vy[f] = p[f * (VT * 3) + 1]; vz[f] = p[f * (VT * 3) + 2]; }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (hh == FT / HF - 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(ACCFREE(a));                   // the accumulator can take the MMAs of item n + NACC
-                        mbar_arrive(EMPTY_V(s));                   // the slot can take the rows of item n + NV
+                for (int f = 0; f < FT; ++f)
+                    if (f < nf) {
+                        float* d = dst + (int64_t)f * V * 3;
+                        d[0] = ox[f]; d[1] = oy[f]; d[2] = oz[f];
+                    }
+            }
+            if ((!MESH || lm_out) && lm_count > 0) {
+                // landmark vertices (the only output in joints-only mode; next to a mesh that goes to peer memory they keep
+                // the joint assembly's reads local)
+                for (int l = lm_slot; l < n_lm; ++l) {
+                    if (l != lm_slot && lm_idx[l] != v0 + gt) continue;
+#pragma unroll
+                    for (int f = 0; f < FT; ++f)
+                        if (f < nf) {
+                            float* o = lm_out + ((int64_t)(f0 + f) * n_lm + l) * 3;
+                            o[0] = ox[f]; o[1] = oy[f]; o[2] = oz[f];
+                        }
+                    if (lm_count == 1) break;
+                }
+            }
+            if (HAS_JX) {
+                // partial of the regressor row over this warp's 32 vertices: 24 sums (8 frames x 3) reduced with a transposed
+                // butterfly - at every level a lane keeps one half of its values and sends the other - 24 shuffles in all;
+                // afterwards lane l holds the sum for frame 4*b4 + 2*b3 + b2 (b = bits of l), component (l & 3), lanes with (l & 3) == 3 idle
+                float r = 0.f;
+                if (any_jx) {
+                    float P[24];
+#pragma unroll
+                    for (int f = 0; f < FT; ++f) { P[f * 3] = wjx * ox[f]; P[f * 3 + 1] = wjx * oy[f]; P[f * 3 + 2] = wjx * oz[f]; }
+                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+                    float Q[12], R6[6], S[4], U[2];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        const float send = b16 ? P[i] : P[i + 12], keep = b16 ? P[i + 12] : P[i];
+                        Q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const float send = b8 ? Q[i] : Q[i + 6], keep = b8 ? Q[i + 6] : Q[i];
+                        R6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float send = b4 ? R6[i] : R6[i + 3], keep = b4 ? R6[i + 3] : R6[i];
+                        S[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    S[3] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float send = b2 ? S[i] : S[i + 2], keep = b2 ? S[i + 2] : S[i];
+                        U[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    {
+                        const float send = b1 ? U[0] : U[1], keep = b1 ? U[1] : U[0];
+                        r = keep + __shfl_xor_sync(0xffffffffu, send, 1);
                     }
                 }
-                float ox[HF], oy[HF], oz[HF];
-#pragma unroll
-                for (int f = 0; f < HF; ++f) {
-                    const uint32_t* q = t + f * 12;
-                    const float x = vx[f], y = vy[f], z = vz[f];
-                    ox[f] = __uint_as_float(q[0]) * x + __uint_as_float(q[1]) * y + __uint_as_float(q[2]) * z + __uint_as_float(q[3]);
-                    oy[f] = __uint_as_float(q[4]) * x + __uint_as_float(q[5]) * y + __uint_as_float(q[6]) * z + __uint_as_float(q[7]);
-                    oz[f] = __uint_as_float(q[8]) * x + __uint_as_float(q[9]) * y + __uint_as_float(q[10]) * z + __uint_as_float(q[11]);
-                }
-                if (MESH && gt < nv) {
-                    float* dst = verts + ((int64_t)fh * V + v0 + gt) * 3;
-#pragma unroll
-                    for (int f = 0; f < HF; ++f)
-                        if (f < nfh) {
-                            float* d = dst + (int64_t)f * V * 3;
-                            d[0] = ox[f]; d[1] = oy[f]; d[2] = oz[f];
-                        }
-                }
-                if ((!MESH || lm_out) && lm_count > 0) {
-                    // landmark vertices (the only output in joints-only mode; next to a mesh that goes to peer memory they
-                    // keep the joint assembly's reads local)
-                    for (int l = lm_slot; l < n_lm; ++l) {
-                        if (l != lm_slot && lm_idx[l] != v0 + gt) continue;
-#pragma unroll
-                        for (int f = 0; f < HF; ++f)
-                            if (f < nfh) {
-                                float* o = lm_out + ((int64_t)(fh + f) * n_lm + l) * 3;
-                                o[0] = ox[f]; o[1] = oy[f]; o[2] = oz[f];
-                            }
-                        if (lm_count == 1) break;
-                    }
-                }
-                if (HAS_JX) {
-                    // partial of the regressor row over this warp's 32 vertices: 12 sums (4 frames x 3) reduced with a
-                    // transposed butterfly - at every level a lane keeps one half of its values and sends the other - 13
-                    // shuffles in all; afterwards lane l holds the sum for frame 2*b16 + b8, component 2*b4 + b2 (b = bits of l)
-                    float r = 0.f;
-                    if (any_jx) {
-                        float P[12];
-#pragma unroll
-                        for (int f = 0; f < HF; ++f) { P[f * 3] = wjx * ox[f]; P[f * 3 + 1] = wjx * oy[f]; P[f * 3 + 2] = wjx * oz[f]; }
-                        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-                        float Q[6], S[4], U[2];
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) {
-                            const float send = b16 ? P[i] : P[i + 6], keep = b16 ? P[i + 6] : P[i];
-                            Q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            const float send = b8 ? Q[i] : Q[i + 3], keep = b8 ? Q[i + 3] : Q[i];
-                            S[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                        }
-                        S[3] = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const float send = b4 ? S[i] : S[i + 2], keep = b4 ? S[i + 2] : S[i];
-                            U[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-                        {
-                            const float send = b2 ? U[0] : U[1], keep = b2 ? U[1] : U[0];
-                            r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                        }
-                        r += __shfl_xor_sync(0xffffffffu, r, 1);
-                    }
-                    const int pf = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1), pc = ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    if ((lane & 1) == 0 && pc < 3 && pf < nfh) jx_partial[((int64_t)(tile * 4 + quad) * F + fh + pf) * 3 + pc] = r;
-                }
+                const int pf = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1), pc = lane & 3;
+                if (pc < 3 && pf < nf) jx_partial[((int64_t)(tile * 4 + quad) * F + f0 + pf) * 3 + pc] = r;
             }
 #pragma unroll
             for (int k = 0; k < NG; ++k) c.next();

@@ -3,7 +3,6 @@
 // Arithmetic restated from smplx==0.1.26 lbs.py (the reference calls it at
 // lib/models/smpl.py:111,113) and lib/models/smpl.py:108-130,149-191.
 #include "common.cuh"
-#include "lbs_layout.cuh"
 #include "geometry.cuh"
 
 namespace gait {
@@ -144,21 +143,21 @@ smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ x6
             reinterpret_cast<float4*>(a)[i] = make_float4(av[i * 4], av[i * 4 + 1], av[i * 4 + 2], av[i * 4 + 3]);
     }
     if (Aop) {
-        // tensor-core LBS operand (lbs_tc.cu, lbs_layout.cuh): per LBS_TC_FT-frame group a blob [hi|lo][kchunk][rowgroup][8][4]
-        // with row n = (f % LBS_TC_FT) * 12 + c, k = joint; values pre-split into TF32 hi/lo.
-        float* blob = Aop + (f / LBS_TC_FT) * (2 * LBS_TC_AOP_PART_FLOATS);
-        const int fl = (int)(f % LBS_TC_FT);
+        // tensor-core LBS operand (lbs_tc.cu): per 8-frame group a blob [hi|lo][kchunk][rowgroup][8][4] with
+        // row n = (f % 8) * 12 + c, k = joint; values pre-split into TF32 hi/lo.
+        float* blob = Aop + (f >> 3) * (2 * 6 * 96 * 4);
+        const int fl = (int)(f & 7);
 #pragma unroll
         for (int c = 0; c < 12; ++c) {
             const int n = fl * 12 + c;
-            const int idx = ((j >> 2) * (LBS_TC_FT * 12 / 8) + (n >> 3)) * 32 + (n & 7) * 4 + (j & 3);
+            const int idx = ((j >> 2) * 12 + (n >> 3)) * 32 + (n & 7) * 4 + (j & 3);
             uint32_t hb;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(av[c]));
             const float hi = __uint_as_float(hb);
             uint32_t lb;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(av[c] - hi));
             blob[idx] = hi;
-            blob[LBS_TC_AOP_PART_FLOATS + idx] = __uint_as_float(lb);
+            blob[6 * 96 * 4 + idx] = __uint_as_float(lb);
         }
     }
     float* jp = J_posed + (f * NJ + j) * 3;

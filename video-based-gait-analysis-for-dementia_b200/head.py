@@ -68,10 +68,14 @@ class GaitHead(nn.Module):
         self._slots, self._graphs = [], []
 
     # ------------------------------------------------------------------ buffers for one (S,T)
-    def _make_plan(self, S: int, T: int, verts_addr: int | None = None):
+    def _make_plan(self, S: int, T: int, verts_addr: int | None = None, parent=None, seq_off: int = 0, front_only: bool = False):
         """Buffers of one (S,T) step.  verts_addr: raw device address that receives the mesh (F,V,3) instead of the plan's own
         output buffer - a slice of a gathered buffer, possibly PEER memory of the root rank (sharding.RootGather): the
-        skinning kernel then also writes the landmark vertices to a local buffer, so that nothing reads the remote mesh."""
+        skinning kernel then also writes the landmark vertices to a local buffer, so that nothing reads the remote mesh.
+        parent / seq_off: a SUB-plan for sequences [seq_off, seq_off + S) of `parent`: it runs only the SMPL stages
+        (_stages(..., part="smpl")) on the parent's regressor state, so one encoder + regressor pass over a whole shard can be
+        followed by several SMPL passes whose outputs leave one after the other (overlapping the gather with compute).
+        front_only: the parent of such sub-plans - encoder + regressor buffers only (no mesh-sized allocations)."""
         dev = self.regressor.fc1.weight.device
         if dev.type != "cuda":
             raise L.GaitLibraryError("GaitHead is on %s; move it to a CUDA device (no CPU path)" % dev)
@@ -83,11 +87,13 @@ class GaitHead(nn.Module):
         e = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.float32)
         gru_bytes = lib.gait_gru_workspace_bytes(S, T, H)
         hmr_bytes = lib.gait_hmr_workspace_bytes(F, self.regressor.fc1.out_features)
+        sub = parent is not None
+        F_all, F = F, (0 if front_only else F)          # SMPL-stage buffers are empty in a front-only plan
         p = {
-            "S": S, "T": T, "F": F, "V": V, "dev": dev,
-            "x": e(S, T, H), "y_raw": e(S, T, H), "enc": e(S, T, H),
-            "ws": e(max(gru_bytes, hmr_bytes, 4) // 4), "gru_bytes": gru_bytes, "hmr_bytes": hmr_bytes,
-            "state": e(F, _STATE_LD), "Jp": e(F, 24, 3),
+            "S": S, "T": T, "F": F_all, "V": V, "dev": dev,
+            "x": None if sub else e(S, T, H), "y_raw": None if sub else e(S, T, H), "enc": None if sub else e(S, T, H),
+            "ws": None if sub else e(max(gru_bytes, hmr_bytes, 4) // 4), "gru_bytes": gru_bytes, "hmr_bytes": hmr_bytes,
+            "state": parent["state"][seq_off * T:(seq_off + S) * T] if sub else e(F_all, _STATE_LD), "Jp": e(F, 24, 3),
             "aop": e(lib.gait_smpl_lbs_aop_bytes(F) // 4),
             "coef": e(F, 224), "v_posed": e(F, 384 * ((V + 127) // 128)),
             # full mesh (F,V,3), or in joints-only mode just the landmark vertices the joint sets read (config 5)
@@ -147,9 +153,14 @@ class GaitHead(nn.Module):
         self._graph = None
         return self._plan
 
-    def _stages(self, p):
+    _FRONT = ("gru", "regressor")
+
+    def _stages(self, p, part: str = "all"):
         """The step as an ordered list of (name, thunk); each thunk enqueues one stage on the
-        current stream through the C-ABI (no allocation, no torch op)."""
+        current stream through the C-ABI (no allocation, no torch op).  part: "all", "front" (encoder + regressor) or
+        "smpl" (everything after the regressor state: chain, blend, skinning, joints)."""
+        if part != "all":
+            return [(n, f) for n, f in self._stages(p) if (n in self._FRONT) == (part == "front")]
         reg, smpl, gru = self.regressor, self.regressor.smpl, self.encoder.gru
         rk, sk = reg._prepare(), smpl._prepare()
         if not (smpl.extra and smpl.kinectv2):
@@ -197,9 +208,9 @@ class GaitHead(nn.Module):
                 ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st()))),
         ]
 
-    def _launch(self, p):
-        """Enqueue one step on the current stream."""
-        for _, fn in self._stages(p):
+    def _launch(self, p, part: str = "all"):
+        """Enqueue one step (or its "front" / "smpl" part) on the current stream."""
+        for _, fn in self._stages(p, part):
             fn()
 
     @torch.no_grad()
@@ -249,19 +260,20 @@ class GaitHead(nn.Module):
             best = min(best, a.elapsed_time(b) / launches)
         return best
 
-    def capture_plan(self, p, warm: bool = True):
-        """Capture one step over the buffers of plan `p` into a CUDA graph (returns it; sets launches_per_step)."""
+    def capture_plan(self, p, warm: bool = True, part: str = "all"):
+        """Capture one step (or one part of it) over the buffers of plan `p` into a CUDA graph (returns it; sets
+        launches_per_step to the launches of what was captured)."""
         if warm:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._launch(p)                  # warm-up outside capture (lazy module loading)
+                self._launch(p, part)            # warm-up outside capture (lazy module loading)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
         n0 = L.launch_count()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._launch(p)
+            self._launch(p, part)
         self.launches_per_step = L.launch_count() - n0
         return g
 

@@ -186,12 +186,15 @@ class RootGather:
       'peer-copy'  : the chunk's mesh is written locally, then put into the root's buffer by an asynchronous peer copy on a
                      second stream (copy engines over NVLink; no SM touches the link)
       'nccl'       : grouped ncclSend/ncclRecv (torch.distributed.batch_isend_irecv) per chunk, waited at the end
+    smpl_chunks > 1 splits only the part AFTER the regressor (chain, blend, skinning, joints) of every sequence chunk: the
+    encoder + regressor run once over the whole chunk (their GEMMs are more efficient on many rows), the meshes are produced
+    and leave in smpl_chunks pieces.
     The root computes its own shard directly into its slice of the gathered buffers in every mode.  A step ends with a
     completion signal (a 1-element all-reduce on the launching stream; host barrier on gloo), after which the root may read
     `gathered()`: {'verts': (S_total,T,V,3), 'kinect25': (S_total,T,25,3)} (joints-only heads: 'kinect25' only)."""
 
     def __init__(self, head, S_total: int, T: int, mode: str = "peer-copy", chunks: int = 1, root: int = 0, group=None,
-                 use_graphs: bool = True):
+                 use_graphs: bool = True, smpl_chunks: int = 1):
         from . import _lib as L
         if mode not in GATHER_MODES:
             raise ValueError(f"mode must be one of {GATHER_MODES}")
@@ -199,6 +202,7 @@ class RootGather:
             raise RuntimeError("RootGather needs an initialised process group")
         self.head, self.mode, self.root, self.group, self.T = head, mode, root, group, T
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.smpl_chunks = max(1, smpl_chunks)
         self.is_root = self.rank == root
         self.S_total = S_total
         self.lo, self.hi = shard_bounds(S_total, self.world, self.rank)
@@ -233,15 +237,41 @@ class RootGather:
             self.kinect_all = view(kin_off, (S_total, T, 25, 3))
         self._mesh_addr = (lambda s: base + s * per_seq_mesh * 4) if (mode != "nccl" or self.is_root) else None
         self._kin_addr = (lambda s: base + kin_off + s * per_seq_kin * 4) if (mode != "nccl" or self.is_root) else None
-        # one plan (+ graph) per chunk; where the mesh of a chunk is written:
-        #   root: its slice of the gathered buffer; peer-store: the root's slice through the mapping; else: the plan's own buffer
-        self.plans, self.graphs = [], []
+        # one unit per sequence chunk: a full plan, or a front plan (encoder + regressor) with smpl_chunks SMPL sub-plans.
+        # where the mesh of a piece is written: root -> its slice of the gathered buffer; peer-store -> the root's slice through
+        # the mapping; else -> the plan's own buffer (then copied).
+        def dest(seq):
+            ok = self.mesh and (self.is_root or mode == "peer-store") and (self._mesh_addr(self.lo + seq) % 8 == 0)
+            return self._mesh_addr(self.lo + seq) if ok else None
+
+        self.units, self.pieces = [], []              # pieces: (plan, graph, first local sequence) in sequence order
+        smpl_chunks = max(1, smpl_chunks)
+        launches, first = 0, True
         for (a, b) in self.cb:
-            direct = self.mesh and (self.is_root or mode == "peer-store")
-            p = head._make_plan(b - a, T, verts_addr=self._mesh_addr(self.lo + a) if direct else None)
-            self.plans.append(p)
-        self.graphs = [head.capture_plan(p, warm=(i == 0)) if use_graphs else None for i, p in enumerate(self.plans)]
-        self.launches_per_step = head.launches_per_step * len(self.plans) if use_graphs else None
+            k = min(smpl_chunks, b - a)
+            if k <= 1:
+                p = head._make_plan(b - a, T, verts_addr=dest(a))
+                g = head.capture_plan(p, warm=first) if use_graphs else None
+                launches += head.launches_per_step if use_graphs else 0
+                unit = {"front": None, "fgraph": None, "x": p["x"], "a": a, "b": b, "pieces": [(p, g, a)]}
+            else:
+                front = head._make_plan(b - a, T, front_only=True)
+                fg = head.capture_plan(front, warm=first, part="front") if use_graphs else None
+                launches += head.launches_per_step if use_graphs else 0
+                unit = {"front": front, "fgraph": fg, "x": front["x"], "a": a, "b": b, "pieces": []}
+                for i in range(k):
+                    sa, sb = shard_bounds(b - a, k, i)
+                    sp = head._make_plan(sb - sa, T, verts_addr=dest(a + sa), parent=front, seq_off=sa)
+                    if first and use_graphs:
+                        head._launch(front, "front")       # the sub-plan's warm-up reads the regressor state
+                    sg = head.capture_plan(sp, warm=first, part="smpl") if use_graphs else None
+                    launches += head.launches_per_step if use_graphs else 0
+                    unit["pieces"].append((sp, sg, a + sa))
+            first = False
+            self.units.append(unit)
+            self.pieces += unit["pieces"]
+        self.plans = [pc[0] for pc in self.pieces]
+        self.launches_per_step = launches if use_graphs else None
         self.copy_stream = torch.cuda.Stream(device=dev)
         self._flag = torch.zeros(1, device=dev, dtype=torch.float32)
         self._L = L
@@ -254,19 +284,30 @@ class RootGather:
         """Copy this rank's (S_local,T,2048) features (host or device) into the chunk input buffers."""
         if x_local.shape[0] != self.S_local:
             raise ValueError(f"rank {self.rank} expects {self.S_local} sequences, got {x_local.shape[0]}")
-        for (a, b), p in zip(self.cb, self.plans):
-            p["x"].copy_(x_local[a:b], non_blocking=True)
+        for u in self.units:
+            u["x"].copy_(x_local[u["a"]:u["b"]], non_blocking=True)
 
-    def _nccl_ops(self, c):
-        a, b = self.cb[c]
-        p = self.plans[c]
+    def _piece_bounds(self, n_local):
+        """[(a, b)] of every piece of a shard of n_local sequences, in order (same rule on every rank)."""
+        out = []
+        for c in range(len(self.cb)):
+            a, b = shard_bounds(n_local, len(self.cb), c)
+            k = min(self.smpl_chunks, b - a)
+            for i in range(max(k, 1)):
+                sa, sb = shard_bounds(b - a, max(k, 1), i)
+                out.append((a + sa, a + sb))
+        return out
+
+    def _nccl_ops(self, i):
+        """send / recv operations of piece i (the i-th piece of every rank's shard)."""
+        p = self.plans[i]
         if self.is_root:
             ops = []
             for r in range(self.world):
                 if r == self.root:
                     continue
                 rlo, rhi = shard_bounds(self.S_total, self.world, r)
-                ca, cb_ = shard_bounds(rhi - rlo, len(self.cb), c)
+                ca, cb_ = self._piece_bounds(rhi - rlo)[i]
                 ops.append(dist.P2POp(dist.irecv, self.kinect_all[rlo + ca: rlo + cb_], r, self.group))
                 if self.mesh:
                     ops.append(dist.P2POp(dist.irecv, self.verts_all[rlo + ca: rlo + cb_], r, self.group))
@@ -283,27 +324,34 @@ class RootGather:
         cur = torch.cuda.current_stream()
         cs = self.copy_stream
         works = []
-        for c, p in enumerate(self.plans):
-            if self.graphs[c] is not None:
-                self.graphs[c].replay()
-            else:
-                self.head._launch(p)
-            a, b = self.cb[c]
-            if self.is_root:
-                # own Kinect-25 joints into the gathered buffer (the mesh was written in place)
-                self._L.call("gait_peer_copy", self._kin_addr(self.lo + a), p["kinect"].data_ptr(), p["kinect"].numel() * 4, cur.cuda_stream)
-            elif self.mode == "nccl":
-                pass
-            else:
-                ev = cur.record_event()
-                cs.wait_event(ev)
-                self._L.call("gait_peer_copy", self._kin_addr(self.lo + a), p["kinect"].data_ptr(), p["kinect"].numel() * 4, cs.cuda_stream)
-                if self.mesh and self.mode == "peer-copy":
-                    self._L.call("gait_peer_copy", self._mesh_addr(self.lo + a), p["verts"].data_ptr(), p["verts"].numel() * 4, cs.cuda_stream)
-            if self.mode == "nccl" and self.world > 1:
-                ops = self._nccl_ops(c)
-                if ops:
-                    works += dist.batch_isend_irecv(ops)
+        i = 0
+        for u in self.units:
+            if u["front"] is not None:
+                if u["fgraph"] is not None:
+                    u["fgraph"].replay()
+                else:
+                    self.head._launch(u["front"], "front")
+            for (p, g, a) in u["pieces"]:
+                if g is not None:
+                    g.replay()
+                else:
+                    self.head._launch(p, "smpl" if u["front"] is not None else "all")
+                if self.is_root:
+                    # own Kinect-25 joints into the gathered buffer (the mesh was written in place unless its slice is misaligned)
+                    self._L.call("gait_peer_copy", self._kin_addr(self.lo + a), p["kinect"].data_ptr(), p["kinect"].numel() * 4, cur.cuda_stream)
+                    if self.mesh and p["verts"] is not None:
+                        self._L.call("gait_peer_copy", self._mesh_addr(self.lo + a), p["verts"].data_ptr(), p["verts"].numel() * 4, cur.cuda_stream)
+                elif self.mode != "nccl":
+                    ev = cur.record_event()
+                    cs.wait_event(ev)
+                    self._L.call("gait_peer_copy", self._kin_addr(self.lo + a), p["kinect"].data_ptr(), p["kinect"].numel() * 4, cs.cuda_stream)
+                    if self.mesh and p["verts"] is not None:       # peer-copy, or a peer-store piece whose slice is misaligned
+                        self._L.call("gait_peer_copy", self._mesh_addr(self.lo + a), p["verts"].data_ptr(), p["verts"].numel() * 4, cs.cuda_stream)
+                if self.mode == "nccl" and self.world > 1:
+                    ops = self._nccl_ops(i)
+                    if ops:
+                        works += dist.batch_isend_irecv(ops)
+                i += 1
         for w in works:
             w.wait()
         cur.wait_stream(cs)
@@ -331,7 +379,7 @@ class RootGather:
 
     def close(self):
         torch.cuda.synchronize()
-        self.graphs, self.plans = [], []
+        self.units, self.pieces, self.plans = [], [], []
         if self.peer is not None:
             self.peer.close()
 
