@@ -212,6 +212,14 @@ int gait_smpl_lbs_tc_joints(const float* v_posed, int64_t ldv, const float* Aop,
 int gait_smpl_lbs_tc_ex(const float* v_posed, int64_t ldv, const float* Aop, const float* Wpack, const float* jx,
                         float* verts, float* jx_partial, const int32_t* lm_idx, int n_lm, float* lm_out, int64_t F,
                         int64_t V, gait_stream_t stream);
+/* Joints-only path without the mesh (BASELINE configs[4]).  Skinning is linear in v_posed for fixed transforms, so the one
+ * regressor row the Kinect-25 set needs (thorax) is  sum_j A[f,j] [P_j coef[f]; s_j]  with P_j (3,224) = sum_v jx[v] W[v,j]
+ * basis[3v..3v+2,:] and s_j = sum_v jx[v] W[v,j] prepared once per model; the landmark vertices are skinned individually.
+ * u (F, ldu >= 3 n_lm + 72) = coef . [basis rows of the landmark vertices (3 n_lm) ; P (72)]^T comes from gait_linear;
+ * A (F,24,12) from the pose chain; lm_weights (n_lm,24) = lbs_weights[landmarks]; s (24).
+ * lm_out (F,n_lm,3) and thorax (F,3) feed gait_joints_assemble (verts = lm_out, V = n_lm, one extra part). */
+int gait_smpl_reduced_joints(const float* A, const float* u, int64_t ldu, const float* lm_weights, const float* s,
+                             float* lm_out, float* thorax, int64_t F, int n_lm, gait_stream_t stream);
 /* vertices2joints (smplx lbs; lib/models/smpl.py:113, pare.py:70-76, spin.py:279-282):
  * out (F,Rj,3) = Jreg (Rj,V) . verts (F,V,3). */
 int gait_joint_regress(const float* verts, const float* Jreg, float* out, int64_t F, int64_t V, int Rj,

@@ -206,6 +206,17 @@ def test_kinect_db_writer_format(tmp_path):
     assert np.array_equal(np.concatenate([d["joints3D"] for d in dbs]), allj)
     with pytest.raises(ValueError):
         KinectDbWriter(str(tmp_path / "db.pkl"))
+    # skipped videos (no annotations, batch_generation.py:246-248) advance the index the shard rule uses: with
+    # MAX_VID = 2 and the list [a, SKIP, b, c, SKIP, d] the reference cuts before idx 2 and idx 4 (6 - 4 = 2 > 1)
+    w = KinectDbWriter(str(tmp_path / "sk.json"), max_videos=2, min_tail=1, total=6)
+    seq = ["a", None, "b", "c", None, "d"]
+    for name in seq:
+        if name is None:
+            w.skip()
+        else:
+            w.add(name + ".avi", rng.standard_normal((2, 25, 3)), rng.standard_normal((2, 4)))
+    dbs = [joblib.load(f) for f in w.close()]
+    assert [sorted(set(d["vid_name"])) for d in dbs] == [["a"], ["b", "c"], ["d"]]
 
 
 def test_strict_load_of_reference_key_set(smpl_data):
@@ -235,3 +246,45 @@ def test_strict_load_of_reference_key_set(smpl_data):
         assert not res.missing_keys and not res.unexpected_keys
         k0 = next(k for k in want if k.endswith("lbs_weights"))
         assert torch.equal(mod.state_dict()[k0], ckpt[k0])
+
+
+def test_smpl_pkl_loader_without_chumpy(tmp_path, smpl_data):
+    """The reference loads data/smpl_data/SMPL_NEUTRAL.pkl through smplx + chumpy (lib/models/smpl.py:102).  A pickle with
+    the official file's structure - chumpy arrays, a scipy-sparse J_regressor, (6890,3,207) posedirs, 300 shape components,
+    kintree_table with 2^32-1 as the root's parent - loads through the stand-in unpickler into the arrays SMPL() is built from."""
+    import pickle
+    import sys
+    import types
+    import scipy.sparse as sp
+    from gaitb200.smpl import load_smpl_data
+    mod = types.ModuleType("chumpy"); ch = types.ModuleType("chumpy.ch")
+
+    class Ch:                                             # minimal stand-in for the class the official pickle refers to
+        def __init__(self, x):
+            self.x = np.asarray(x)
+
+        def __getstate__(self):
+            return {"x": self.x, "_dirty_vars": set()}
+    Ch.__module__, Ch.__qualname__ = "chumpy.ch", "Ch"
+    ch.Ch = Ch; mod.ch = ch
+    sys.modules["chumpy"], sys.modules["chumpy.ch"] = mod, ch
+    try:
+        V = 6890
+        rng = np.random.default_rng(0)
+        shapedirs300 = np.concatenate([smpl_data["shapedirs"], rng.standard_normal((V, 3, 290)).astype(np.float32)], axis=2)
+        posedirs_v3p = smpl_data["posedirs"].T.reshape(V, 3, 207)
+        kintree = np.stack([smpl_data["parents"].astype(np.int64) % (2 ** 32), np.arange(24)])
+        raw = {"v_template": Ch(smpl_data["v_template"]), "shapedirs": Ch(shapedirs300), "posedirs": Ch(posedirs_v3p),
+               "J_regressor": sp.csc_matrix(smpl_data["J_regressor"]), "weights": Ch(smpl_data["lbs_weights"]),
+               "f": smpl_data["faces"].astype(np.uint32), "kintree_table": kintree.astype(np.uint32), "J": Ch(np.zeros((24, 3)))}
+        d = tmp_path / "smpl_data"; d.mkdir()
+        with open(d / "SMPL_NEUTRAL.pkl", "wb") as f:
+            pickle.dump(raw, f, protocol=2)
+        np.save(d / "J_regressor_extra.npy", smpl_data["J_regressor_extra"])
+    finally:
+        del sys.modules["chumpy"], sys.modules["chumpy.ch"]          # loading must not need chumpy
+    got = load_smpl_data(d)
+    for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights", "J_regressor_extra"):
+        assert np.array_equal(np.asarray(got[k], dtype=np.float32), np.asarray(smpl_data[k], dtype=np.float32)), k
+    assert np.array_equal(got["parents"], smpl_data["parents"]) and np.array_equal(got["faces"], smpl_data["faces"])
+    assert np.array_equal(got["landmark_verts"], smpl_data["landmark_verts"])

@@ -535,27 +535,41 @@ def test_fused_chain_entry_is_bit_identical(smpl_data, lib_loaded):
         assert torch.equal(a, b)
 
 
-def test_head_joints_only_c5(lib_loaded):
-    """BASELINE config 5: the joints-only path (mesh never written to HBM) gives bit-identical joints, Kinect-25
-    joints, kp_2d and theta to the full-mesh path on the same inputs, and agrees with the oracle."""
+@pytest.mark.parametrize("variant", ["sparse", "dense"])
+def test_head_joints_only_c5(variant, lib_loaded):
+    """BASELINE config 5, both joints-only modes (the mesh is never written to HBM).  "skin": every vertex is skinned on chip;
+    joints, Kinect-25 joints, kp_2d and theta are bit-identical to the full-mesh path.  "reduced": only the landmark vertices
+    are formed and the thorax regressor row is folded through the skinning weights (linearity of LBS in v_posed); it agrees
+    with the full-mesh path to FP32 rounding (different summation order) and with the oracle within tolerance, for SMPL-like
+    sparse and for fully dense skin weights / regressor rows."""
     from gaitb200.head import GaitHead
     from oracle.head import GaitHeadOracle
-    data = synthetic.make_smpl_data(seed=0, variant="sparse")
+    data = synthetic.make_smpl_data(seed=0, variant=variant)
     mean = synthetic.make_mean_params()
     rs = synthetic.make_regressor_state(seed=0, decoder_gain=0.3)
     gs = synthetic.make_gru_state(seed=0)
     full = GaitHead(data, mean, rs, gs).cuda()
+    skin = GaitHead(data, mean, rs, gs, write_mesh=False, joints_mode="skin").cuda()
     lean = GaitHead(data, mean, rs, gs, write_mesh=False).cuda()
+    assert lean.joints_mode == "reduced"
     for S, T_ in [(3, 7), (8, 16)]:
         feats = synthetic.make_features(S, T_, seed=77)
         a = {k: v.clone() for k, v in full(feats.cuda()).items()}
-        b = {k: v.clone() for k, v in lean(feats.cuda()).items()}
-        assert "verts" not in b and lean._plan["verts"] is None
+        b = {k: v.clone() for k, v in skin(feats.cuda()).items()}
+        c = {k: v.clone() for k, v in lean(feats.cuda()).items()}
+        assert "verts" not in b and skin._plan["verts"] is None
+        assert "verts" not in c and lean._plan["v_posed"].numel() == 0           # no mesh-sized buffer at all
         for k in ("kp_3d", "kinect25", "kp_2d", "theta", "rotmat"):
             assert torch.equal(a[k], b[k]), k
+        for k in ("theta", "rotmat"):
+            assert torch.equal(a[k], c[k]), k
+        assert maxerr(c["kp_3d"], a["kp_3d"]) <= 5e-6 and maxerr(c["kinect25"], a["kinect25"]) <= 5e-6
+        assert maxerr(c["kp_2d"], a["kp_2d"]) <= 2e-5
         ref = GaitHeadOracle(data, mean, rs, gs)(feats)
-        assert maxerr(b["kinect25"], ref["kinect25"]) <= TOL_V
-        assert maxerr(b["kp_2d"], ref["kp_2d"]) <= TOL_2D
+        for o in (b, c):
+            assert maxerr(o["kinect25"], ref["kinect25"]) <= TOL_V
+            assert maxerr(o["kp_3d"], ref["kp_3d"]) <= TOL_V
+            assert maxerr(o["kp_2d"], ref["kp_2d"]) <= TOL_2D
 
 
 def _oracle_chunked(oracle, feats, fp64=False, chunk=128):

@@ -64,6 +64,7 @@ _SIGS = {
     "gait_peer_open": [C.c_char_p, C.POINTER(P)],
     "gait_peer_close": [P],
     "gait_peer_copy": [P, P, SZ, P],
+    "gait_smpl_reduced_joints": [P, P, I64, P, P, P, P, I64, I32, P],
     "gait_joint_regress": [P, P, P, I64, I64, I32, P],
     "gait_joint_regress_pack_bytes": [I64, I32],
     "gait_joint_regress_pack": [P, P, I64, I32, P],

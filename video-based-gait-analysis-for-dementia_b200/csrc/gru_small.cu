@@ -101,11 +101,10 @@ gru_small_kernel(const float* __restrict__ gi, const float* __restrict__ W_hh, c
                 SpinGuard guard;
                 for (;;) {
                     unsigned v;
-                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(fl) : "memory");
                     if (v >= (unsigned)step) break;
                     guard.tick();
                 }
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
             }
             __syncthreads();
             const int tp = reverse ? t + 1 : t - 1;
@@ -161,10 +160,8 @@ gru_small_kernel(const float* __restrict__ gi, const float* __restrict__ W_hh, c
         }
         if (step < T - 1) {
             __syncthreads();                       // the CTA's 16 units of h_t are stored; everyone is done reading hs
-            if (tid == 0) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + (size_t)blockIdx.x * FLAG_STRIDE), "r"((unsigned)(step + 1)) : "memory");
-            }
+            if (tid == 0)           // release: cumulative over the CTA's stores of h_t ordered before it by the barrier
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + (size_t)blockIdx.x * FLAG_STRIDE), "r"((unsigned)(step + 1)) : "memory");
         }
     }
 }

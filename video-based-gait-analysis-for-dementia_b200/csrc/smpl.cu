@@ -433,7 +433,58 @@ __global__ void pack_theta_kernel(const float* __restrict__ R, const float* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Joints-only skinning (BASELINE configs[4]) without the mesh.  The Kinect-25 set needs only the n_lm landmark vertices
+// and ONE regressor row (thorax) over all vertices.  Skinning is linear in v_posed for fixed transforms,
+//     thorax[f] = sum_v jx[v] T[f,v] [v_posed[f,v]; 1] = sum_j A[f,j] [ P_j coef[f] ; s_j ],
+//     P_j (3 x 224) = sum_v jx[v] W[v,j] basis[3v..3v+2, :],   s_j = sum_v jx[v] W[v,j]      (once per model),
+// so a (F x (3 n_lm + 72) x 224) GEMM u = coef . [basis rows of the landmarks ; P]^T replaces the 20 670-column blend GEMM and
+// this kernel replaces the skinning pass: one thread per (frame, landmark) applies the dense 24-joint blend of its vertex,
+// one thread per frame combines the 24 weighted centroids.  No vertex other than the landmarks is ever formed.
+// A (F,24,12); u (F, ldu): [landmark v_posed (n_lm x 3) | centroids (24 x 3)]; lm_weights (n_lm, 24); s (24).
+// ------------------------------------------------------------------------------------------
+__global__ void smpl_reduced_joints_kernel(const float* __restrict__ A, const float* __restrict__ u, int64_t ldu,
+                                           const float* __restrict__ lm_weights, const float* __restrict__ s,
+                                           float* __restrict__ lm_out, float* __restrict__ thorax, int64_t F, int n_lm) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int per = n_lm + 1;
+    if (i >= F * per) return;
+    const int64_t f = i / per;
+    const int l = (int)(i % per);
+    const float* a = A + f * NJ * 12;
+    const float* uf = u + f * ldu;
+    if (l < n_lm) {
+        float T[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = 0.f;
+        const float* w = lm_weights + l * NJ;
+        for (int j = 0; j < NJ; ++j) {
+            const float wj = w[j];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) T[k] = fmaf(wj, a[j * 12 + k], T[k]);
+        }
+        const float x = uf[l * 3], y = uf[l * 3 + 1], z = uf[l * 3 + 2];
+        float* o = lm_out + (f * n_lm + l) * 3;
+        o[0] = T[0] * x + T[1] * y + T[2] * z + T[3];
+        o[1] = T[4] * x + T[5] * y + T[6] * z + T[7];
+        o[2] = T[8] * x + T[9] * y + T[10] * z + T[11];
+    } else {
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        const float* p = uf + n_lm * 3;
+        for (int j = 0; j < NJ; ++j) {
+            const float x = p[j * 3], y = p[j * 3 + 1], z = p[j * 3 + 2], sj = s[j];
+            const float* t = a + j * 12;
+            o0 += t[0] * x + t[1] * y + t[2] * z + t[3] * sj;
+            o1 += t[4] * x + t[5] * y + t[6] * z + t[7] * sj;
+            o2 += t[8] * x + t[9] * y + t[10] * z + t[11] * sj;
+        }
+        thorax[f * 3] = o0; thorax[f * 3 + 1] = o1; thorax[f * 3 + 2] = o2;
+    }
+}
+
 }  // namespace gait
+
+
 
 using namespace gait;
 
@@ -528,6 +579,17 @@ int gait_pack_theta(const float* R, const float* cam, int64_t ldcam, const float
     GAIT_REQUIRE(R && cam && betas && theta && ldcam >= 3 && ldb >= NB, "pack_theta: null pointer or bad stride");
     pack_theta_kernel<<<(unsigned)ceil_div(F * 32, 256), 256, 0, as_stream(stream)>>>(R, cam, ldcam, betas, ldb, theta, F);
     return check_launch("pack_theta");
+}
+
+int gait_smpl_reduced_joints(const float* A, const float* u, int64_t ldu, const float* lm_weights, const float* s,
+                             float* lm_out, float* thorax, int64_t F, int n_lm, gait_stream_t stream) {
+    GAIT_REQUIRE(F >= 0 && n_lm > 0 && n_lm <= 1024, "smpl_reduced_joints: bad sizes");
+    if (F == 0) return GAIT_OK;
+    GAIT_REQUIRE(A && u && lm_weights && s && lm_out && thorax, "smpl_reduced_joints: null pointer");
+    GAIT_REQUIRE(ldu >= 3 * n_lm + 3 * GAIT_NUM_JOINTS, "smpl_reduced_joints: ldu < 3 n_lm + 72");
+    const int64_t n = F * (n_lm + 1);
+    smpl_reduced_joints_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(A, u, ldu, lm_weights, s, lm_out, thorax, F, n_lm);
+    return check_launch("smpl_reduced_joints");
 }
 
 }  // extern "C"

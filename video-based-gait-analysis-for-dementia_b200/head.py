@@ -45,10 +45,17 @@ class HostOutputs(dict):
 
 class GaitHead(nn.Module):
     def __init__(self, smpl_data, mean_params, regressor_state=None, gru_state=None, write_mesh=True,
-                 n_iter=3, fold_regressor=False, **encoder_kw):
+                 n_iter=3, fold_regressor=False, joints_mode="reduced", **encoder_kw):
         """fold_regressor: run the regressor loop as its folded affine map (Regressor.fold; opt-in, same outputs up to FP32
-        rounding, the iteration's GEMMs are gone - not the default and not what bench.py's headline measures)."""
+        rounding, the iteration's GEMMs are gone - not the default and not what bench.py's headline measures).
+        joints_mode (write_mesh=False only): "reduced" - the Kinect-25 set needs 21 landmark vertices and one regressor row
+        (thorax); skinning is linear in v_posed, so that row is folded through the skinning weights once per model and NO
+        vertex other than the landmarks is ever formed (SMPL._prepare_reduced, gait_smpl_reduced_joints); "skin" - every
+        vertex is blended and skinned on chip and only the landmarks / the thorax partials are written."""
         super().__init__()
+        if joints_mode not in ("reduced", "skin"):
+            raise ValueError("joints_mode must be 'reduced' or 'skin'")
+        self.joints_mode = joints_mode
         self.fold_regressor = bool(fold_regressor)
         self.encoder = TemporalEncoder(**encoder_kw)
         self.regressor = Regressor(mean_params, smpl_data)
@@ -103,6 +110,13 @@ class GaitHead(nn.Module):
         }
         if verts_addr is not None and not self.write_mesh:
             raise L.GaitLibraryError("verts_addr given to a joints-only head")
+        self_reduced = (not self.write_mesh) and self.joints_mode == "reduced"
+        if self_reduced:
+            rk = self.regressor.smpl._prepare_reduced()
+            p["A12"] = e(F, 24, 12)                       # skinning transforms as plain 3x4 rows (the reduced path has no tensor-core operand)
+            p["red_u"] = e(F, rk["red_ld"])
+            p["v_posed"] = e(0)                           # never formed
+            p["extra"] = e(1, F, 1, 3)
         external = verts_addr is not None
         local_lm = external or not self.write_mesh
         n_lm = self.regressor.smpl._prepare()["n_landmarks"]
@@ -172,17 +186,28 @@ class GaitHead(nn.Module):
         betas, cam = state + 4 * 144, state + 4 * 154
         L.prepare_weight(gru.weight_ih_l0)
         fk = reg.fold(self.n_iter) if self.fold_regressor else None
-        return [
-            ("gru", lambda: call(
-                "gait_gru_layer", ptr(p["x"]), H, ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), ptr(gru.bias_ih_l0),
-                ptr(gru.bias_hh_l0), None, ptr(p["y_raw"]), H, ptr(p["x"]), H, ptr(p["enc"]), H, None, S, T, H, H, 0,
-                ptr(p["ws"]), p["gru_bytes"], st())),
-            ("regressor", (lambda: call(
-                "gait_hmr_regressor_folded", ptr(p["enc"]), H, ptr(fk["Wf"]), ptr(fk["bf"]), ptr(p["state"]), F, rk["din"],
-                ptr(p["ws"]), p["hmr_bytes"], st())) if self.fold_regressor else lambda: call(
-                "gait_hmr_regressor", ptr(p["enc"]), H, ptr(rk["W1x"]), ptr(rk["W1s"]), ptr(rk["b1"]), ptr(rk["W2"]),
-                ptr(rk["b2"]), ptr(rk["Wd"]), ptr(rk["bd"]), ptr(rk["init"]), 1, self.n_iter, ptr(p["state"]), F,
-                rk["din"], rk["dh"], ptr(p["ws"]), p["hmr_bytes"], st())),
+        if "red_u" in p:
+            # joints-only without the mesh: chain (plain transforms), one small GEMM, landmark skinning + thorax, assembly
+            rd = smpl._prepare_reduced()
+            front = self._front_stages(p, fk, rk, H, S, T, F)
+            return front + [
+                ("pose_chain", lambda: call(
+                    "gait_smpl_pose_chain_rot6d", state, _STATE_LD, 1e-6, betas, _STATE_LD, cam, _STATE_LD, ptr(sk["J_template"]),
+                    ptr(sk["J_shapedirs"]), ptr(sk["parents"]), ptr(p["rotmat"]), ptr(p["A12"]), ptr(p["Jp"]), ptr(p["coef"]), None,
+                    ptr(p["theta"]), F, st())),
+                ("blend", lambda: call(
+                    "gait_linear", ptr(p["coef"]), 224, ptr(rd["red_basis"]), 224, None, None, 0, ptr(p["red_u"]), rd["red_ld"],
+                    F, rd["red_ld"], 224, st())),
+                ("lbs", lambda: call(
+                    "gait_smpl_reduced_joints", ptr(p["A12"]), ptr(p["red_u"]), rd["red_ld"], ptr(rd["lm_weights"]), ptr(rd["red_s"]),
+                    ptr(p["lm_verts"]), ptr(p["extra"]), F, sk["n_landmarks"], st())),
+                ("joints", lambda: call(
+                    "gait_joints_assemble", ptr(p["Jp"]), ptr(p["lm_verts"]), sk["n_landmarks"], ptr(p["lm_iota"]), sk["n_landmarks"],
+                    ptr(p["extra"]), 1, 1, F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
+                    5000., 224., 112.,
+                    ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st())),
+            ]
+        return self._front_stages(p, fk, rk, H, S, T, F) + [
             # rot6d -> R, kinematic chain, blend coefficients, skinning operand and theta in ONE launch
             ("pose_chain", lambda: call(
                 "gait_smpl_pose_chain_rot6d", state, _STATE_LD, 1e-6, betas, _STATE_LD, cam, _STATE_LD, ptr(sk["J_template"]),
@@ -206,6 +231,23 @@ class GaitHead(nn.Module):
                 ptr(p["extra"]), 1, sk["vtiles"], F * 3, ptr(sk["map_kinect"]), 29, ptr(p["joints"]), cam, _STATE_LD,
                 5000., 224., 112.,
                 ptr(p["kp2d"]), ptr(p["gather"]), 25, ptr(p["kinect"]), F, st()))),
+        ]
+
+    def _front_stages(self, p, fk, rk, H, S, T, F):
+        """encoder + regressor stages (shared by the full-mesh / skinned and the reduced joints-only step)"""
+        gru = self.encoder.gru
+        ptr, call, st = L.ptr, L.call, L.stream_ptr
+        return [
+            ("gru", lambda: call(
+                "gait_gru_layer", ptr(p["x"]), H, ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), ptr(gru.bias_ih_l0),
+                ptr(gru.bias_hh_l0), None, ptr(p["y_raw"]), H, ptr(p["x"]), H, ptr(p["enc"]), H, None, S, T, H, H, 0,
+                ptr(p["ws"]), p["gru_bytes"], st())),
+            ("regressor", (lambda: call(
+                "gait_hmr_regressor_folded", ptr(p["enc"]), H, ptr(fk["Wf"]), ptr(fk["bf"]), ptr(p["state"]), F, rk["din"],
+                ptr(p["ws"]), p["hmr_bytes"], st())) if self.fold_regressor else lambda: call(
+                "gait_hmr_regressor", ptr(p["enc"]), H, ptr(rk["W1x"]), ptr(rk["W1s"]), ptr(rk["b1"]), ptr(rk["W2"]),
+                ptr(rk["b2"]), ptr(rk["Wd"]), ptr(rk["bd"]), ptr(rk["init"]), 1, self.n_iter, ptr(p["state"]), F,
+                rk["din"], rk["dh"], ptr(p["ws"]), p["hmr_bytes"], st())),
         ]
 
     def _launch(self, p, part: str = "all"):

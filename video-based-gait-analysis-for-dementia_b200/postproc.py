@@ -104,32 +104,52 @@ def convert_crop_coords_to_orig_img(bbox, keypoints, crop_size):
 class KinectDbWriter:
     """The Kinect-25 database batch_generation.py writes (batch_generation.py:226-238,262-283; doc/batch_generation.md:6-10):
     a joblib dump of {'vid_name': (N,) str, 'bbox': (N,4) float32, 'joints3D': (N,25,3) float32}, one entry per frame in
-    temporal order, split into `<stem>_<k>.json` shards every `max_videos` videos (the reference's MAX_VID) with the
-    remainder in the last shard.  `add` accepts the head's `kinect25` output as a CUDA tensor (one device-to-host copy per
+    temporal order, split into `<stem>_<k>.json` shards every `max_videos` entries of the video list (the reference's
+    MAX_VID; skipped videos count, `skip()`) with the remainder in the last shard.  `add` accepts the head's `kinect25` output as a CUDA tensor (one device-to-host copy per
     video) or a numpy array; this is host-side data-format code, no arithmetic."""
 
-    def __init__(self, outpath: str, max_videos: int = 300, min_tail: int = 10):
+    def __init__(self, outpath: str, max_videos: int = 300, min_tail: int = 10, total: int | None = None):
+        """total: len(vidnames) of the reference's loop, INCLUDING videos that will be skipped; the reference cuts a shard at
+        the top of iteration idx when idx % MAX_VID == 0, idx > 0 and len(vidnames) - idx > 10 (batch_generation.py:226)."""
         if not outpath.endswith(".json"):
             raise ValueError("outpath must end with .json (batch_generation.py:235)")
         self.outpath, self.max_videos, self.min_tail = outpath, int(max_videos), int(min_tail)
+        self.total = None if total is None else int(total)
         self._db = {"vid_name": [], "bbox": [], "joints3D": []}
-        self._videos = 0
+        self._idx = 0                                 # the reference's enumerate index: counts skipped videos too
         self.files = []
+
+    def _top_of_iteration(self, videos_left):
+        """The reference's shard cut, evaluated before video self._idx is processed or skipped."""
+        idx = self._idx
+        if videos_left is not None:
+            remaining = videos_left + 1               # len(vidnames) - idx
+        elif self.total is not None:
+            remaining = self.total - idx
+        else:
+            remaining = None                          # unknown length: always cut
+        if idx > 0 and idx % self.max_videos == 0 and (remaining is None or remaining > self.min_tail):
+            self._flush()
+        self._idx += 1
+
+    def skip(self, videos_left: int | None = None):
+        """A video without annotations (batch_generation.py:246-248 `continue`): nothing is stored, but it advances the
+        enumerate index the shard rule is evaluated on, exactly as in the reference."""
+        self._top_of_iteration(videos_left)
 
     def add(self, vid_name: str, joints3d, bbox, videos_left: int | None = None):
         """One video: joints3d (frames,25,3) [any shape with frames*75 elements], bbox (frames,4).  `videos_left`: how many
-        videos follow (the reference only cuts a shard when more than `min_tail` remain)."""
+        entries of the video list follow this one (alternative to `total`; the reference only cuts a shard when more than
+        `min_tail` remain, counting the current one)."""
         if torch.is_tensor(joints3d):
             joints3d = joints3d.detach().to("cpu", torch.float32).numpy()
         bbox = np.asarray(bbox.detach().cpu().numpy() if torch.is_tensor(bbox) else bbox)
         n = bbox.reshape(-1, 4).shape[0]
         j = np.asarray(joints3d).reshape(n, 25, 3)
-        if self._videos and self._videos % self.max_videos == 0 and (videos_left is None or videos_left + 1 > self.min_tail):
-            self._flush()
+        self._top_of_iteration(videos_left)
         self._db["vid_name"].extend([vid_name.split(".")[0]] * n)
         self._db["bbox"].append(bbox.reshape(n, 4))
         self._db["joints3D"].append(j)
-        self._videos += 1
 
     def _flush(self):
         import joblib

@@ -68,22 +68,36 @@ _KINECT_HAND_JOINTS = [35, 37, 40, 42]                                # smpl.py:
 
 
 def load_smpl_data(model_path) -> dict:
-    """Accept a dict of arrays, an .npz file, or a directory holding SMPL_NEUTRAL*.npz
-    (+ J_regressor_extra.npy).  The reference unpickles SMPL_NEUTRAL.pkl through smplx/chumpy;
-    offline that file does not exist, so the synthetic stand-ins (gaitb200.synthetic) use .npz."""
+    """Accept a dict of arrays, an .npz file, the reference's own SMPL_NEUTRAL.pkl (lib/models/smpl.py:102 unpickles it through
+    smplx + chumpy; here a stand-in unpickler reads the same file without either, scripts/convert_smpl_pkl.py), or a
+    directory holding SMPL_NEUTRAL*.npz / SMPL_NEUTRAL.pkl (+ J_regressor_extra.npy, as in data/smpl_data/)."""
     if isinstance(model_path, dict):
         return model_path
     p = Path(model_path)
+
+    def read(f):
+        if f.suffix == ".pkl":
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_convert_smpl_pkl", Path(__file__).resolve().parent.parent / "scripts" / "convert_smpl_pkl.py")
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod.smpl_pkl_to_dict(f)
+        return dict(np.load(f, allow_pickle=False))
+
     if p.is_dir():
-        cands = sorted(p.glob("SMPL_NEUTRAL*.npz"))
+        cands = sorted(p.glob("SMPL_NEUTRAL*.npz")) or sorted(p.glob("SMPL_NEUTRAL*.pkl"))
         if not cands:
-            raise FileNotFoundError(f"no SMPL_NEUTRAL*.npz under {p}")
-        data = dict(np.load(cands[0], allow_pickle=False))
+            raise FileNotFoundError(f"no SMPL_NEUTRAL*.npz / SMPL_NEUTRAL*.pkl under {p}")
+        data = read(cands[0])
         extra = p / "J_regressor_extra.npy"
         if "J_regressor_extra" not in data and extra.exists():
             data["J_regressor_extra"] = np.load(extra)
         return data
-    return dict(np.load(p, allow_pickle=False))
+    data = read(p)
+    extra = p.parent / "J_regressor_extra.npy"
+    if "J_regressor_extra" not in data and extra.exists():
+        data["J_regressor_extra"] = np.load(extra)
+    return data
 
 
 class _VertexJointSelector(nn.Module):
@@ -185,6 +199,34 @@ class SMPL(nn.Module):
         L.prepare_weight(self._packed["basis_t"])   # constant blend-GEMM operand: TF32 lo part split off once
         self._packed_key = key
         return self._packed
+
+    def _prepare_reduced(self):
+        """Operands of the joints-only path that never forms the mesh (gait_smpl_reduced_joints): the blend-basis rows of the
+        landmark vertices, and the thorax row of J_regressor_extra folded through the skinning weights,
+        P_j = sum_v jx[v] W[v,j] basis[3v..3v+2,:] (24 x 3 x 224) and s_j = sum_v jx[v] W[v,j] - both regressions run on this
+        library's own joint-regression kernel.  red_basis (3 n_lm + 72 -> padded to a multiple of 4, 224)."""
+        pk = self._prepare()
+        if "red_basis" in pk:
+            return pk
+        dev, V, st = pk["basis_t"].device, pk["V"], L.stream_ptr()
+        lm, n_lm = pk["landmarks"].long(), pk["n_landmarks"]
+        rows = (lm[:, None] * 3 + torch.arange(3, device=dev)[None, :]).reshape(-1)
+        jxw = (pk["extra_thorax"].reshape(V, 1) * pk["lbs_weights"]).t().contiguous()            # (24, V): jx[v] W[v,j]
+        basis_fvc = pk["basis_t"].reshape(V, 3, 224).permute(2, 0, 1).contiguous()              # (224, V, 3)
+        Pk = torch.empty(224, NUM_JOINTS, 3, device=dev)
+        L.call("gait_joint_regress", L.ptr(basis_fvc), L.ptr(jxw), L.ptr(Pk), 224, V, NUM_JOINTS, st)
+        ones = torch.ones(1, V, 3, device=dev)
+        sj = torch.empty(1, NUM_JOINTS, 3, device=dev)
+        L.call("gait_joint_regress", L.ptr(ones), L.ptr(jxw), L.ptr(sj), 1, V, NUM_JOINTS, st)
+        n_rows = 3 * n_lm + 3 * NUM_JOINTS
+        red = torch.zeros((n_rows + 3) // 4 * 4, 224, device=dev)
+        red[:3 * n_lm] = pk["basis_t"][rows]
+        red[3 * n_lm:n_rows] = Pk.permute(1, 2, 0).reshape(3 * NUM_JOINTS, 224)
+        pk["red_basis"], pk["red_ld"] = red, red.shape[0]
+        pk["red_s"] = sj[0, :, 0].contiguous()
+        pk["lm_weights"] = pk["lbs_weights"][lm].contiguous()
+        L.prepare_weight(pk["red_basis"])
+        return pk
 
     def _apply(self, fn, *a, **k):
         self._packed = None
