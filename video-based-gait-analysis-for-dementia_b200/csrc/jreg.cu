@@ -31,9 +31,15 @@ using namespace tcu;
 constexpr int FB = 32;                 // frames per cluster (lane = frame)
 constexpr int CL = 8;                  // CTAs per cluster = vertex-range splits
 constexpr int GS = 12;                 // 4-vertex groups per stage (48 vertices, 576 B per frame row)
-constexpr int NW = 6;                  // warps per CTA, GS / NW groups each per stage
+#ifndef GAIT_JREG_NW
+#define GAIT_JREG_NW 6
+#endif
+constexpr int NW = GAIT_JREG_NW;       // warps per CTA, GS / NW groups each per stage
 constexpr int GPW = GS / NW;
-constexpr int D = 4;                   // pipeline stages
+#ifndef GAIT_JREG_D
+#define GAIT_JREG_D 4
+#endif
+constexpr int D = GAIT_JREG_D;         // pipeline stages
 constexpr int THREADS = NW * 32;
 constexpr int XROW = GS * 12;          // floats per frame row per stage
 constexpr int XPITCH = XROW + 4;       // 148: (pitch / 4) odd -> 8 rows hit 8 distinct 16-byte bank groups

@@ -5,27 +5,32 @@
 // Both operands are K-major FP32 in global memory (torch Linear / GRU layout).  Per k-block of 32
 // floats (= one 128-byte swizzle span) the pipeline is
 //
-//   TMA producers (2 warps)      cp.async.bulk.tensor 2D, SWIZZLE_128B, 32-row boxes, one lane per box -> raw P/Q tiles
-//   converter warps (4 warps)    split x = hi + lo with hi = the raw FP32 word (the tensor core ignores the low 13
-//                                mantissa bits = truncation) and lo = RN_tf32(x - trunc(x)): |x - hi - lo| <= 2^-22 |x|.
-//                                P (the 128-row operand): each thread moves its row from smem into TENSOR MEMORY
-//                                (tcgen05.st: columns [hi 32 | lo 32] of the stage), so the MMAs read it from TMEM and
-//                                neither P_hi nor P_lo is ever written to or re-read from shared memory;
-//                                Q: only the lo tile is written (elementwise, so the TMA swizzle pattern is preserved).
+//   TMA producers (2 warps)      cp.async.bulk.tensor 2D, SWIZZLE_128B, 64-row boxes, one lane per box, even / odd k-blocks
+//                                -> raw P / Q tiles (for prepared weights: the hi tile and the lo tile of Q)
+//   converters (2 groups of 4 warps, even / odd k-blocks)
+//                                P (the 128-row operand): each thread moves its row from smem into TENSOR MEMORY, split
+//                                round-to-nearest hi = RN_tf32(x), lo = RN_tf32(x - hi) (tcgen05.st: columns [hi 32 | lo 32]
+//                                of the stage), so the MMAs read it from TMEM and neither P_hi nor P_lo is ever written to
+//                                or re-read from shared memory;
+//                                Q: nothing when the weight was prepared (QLO: both tiles arrive by TMA); otherwise only the
+//                                lo tile is written, lo = RN_tf32(x - trunc(x)) with hi = the raw FP32 word (the tensor core
+//                                ignores the low 13 mantissa bits), elementwise, so the TMA swizzle pattern is preserved.
 //                                Shared-memory bandwidth (LDS/STS + UMMA operand reads share one 128 B/clk pipe,
-//                                ncu: 97 % busy before this change) is what bounds this kernel, not the tensor pipe.
-//   MMA issuer (1 thread)        per 8-wide k-step three tcgen05.mma.kind::tf32 (A operand in TMEM) into one TMEM
-//                                accumulator: P_lo.Q_hi + P_hi.Q_lo + P_hi.Q_hi
-//   promotion warps (4 warps)     every 2 k-blocks: tcgen05.ld 32x32b of the TMEM partial sum, added
-//                                (round-to-nearest) into FP32 registers; two TMEM buffers alternate.
-//                                Final: +bias +Cin -> coalesced global stores
+//                                ncu: 97 % busy before the operand moved to TMEM) bounded the first version.
+//   MMA issuers (2 warps, even / odd accumulator chunks; one lane issues)
+//                                per 8-wide k-step three tcgen05.mma.kind::tf32 (A operand in TMEM) into one TMEM
+//                                accumulator: P_lo.Q_hi + P_hi.Q_lo + P_hi.Q_hi (cross terms first)
+//   promotion warps (8 warps, 120 registers via setmaxnreg)
+//                                every 1 or 2 k-blocks (call-site policy, LinearPromote): tcgen05.ld 32x32b of the TMEM
+//                                partial sum, added (round-to-nearest) into FP32 registers; the TMEM buffers alternate.
+//                                Final: +bias +Cin -> vectorised global stores
 //
-// with mbarrier full/converted/empty rings (3 stages) and accumulator full/empty rings (4 TMEM buffers);
-// CTAs are persistent (one per SM) and walk (tile, k-split) work items, so the stores of one item overlap the
-// loads and MMAs of the next.  Dropped term:
-// P_lo.Q_lo ~ 2^-22 relative.  The same kernel serves C = A.W^T (P = A) and the transposed
-// form (P = W, Q = A) that keeps 128 TMEM lanes busy when A has few rows (GRU recurrence,
-// S = 64); split-K over blockIdx.z writes partial sums that the consumer adds.
+// with mbarrier landed / converted / empty rings (4 stages for BN = 128, 4-6 for BN = 64; even counts so that every warp of a
+// pair always returns to the same stages and sees each barrier phase) and accumulator full / empty rings; CTAs are persistent
+// (one per SM) and walk (tile, k-split) work items in weight-tile-major order, so the stores of one item overlap the loads
+// and MMAs of the next.  Dropped term: P_lo.Q_lo ~ 2^-22 relative.  The same kernel serves C = A.W^T (P = A) and the
+// transposed form (P = W, Q = A) that keeps 128 TMEM lanes busy when A has few rows; split-K work items write partial sums
+// that the consumer adds.  Details and measurements: the kernel comment below and DESIGN.md 4.1 / 4.2.
 #include <cuda.h>
 #include <stdlib.h>
 
