@@ -13,7 +13,7 @@ from gaitb200.head import GaitHead
 L.require_device()
 jo = os.environ.get("LBS_JOINTS_ONLY") == "1"
 head = GaitHead(synthetic.make_smpl_data(seed=0, variant="sparse"), synthetic.make_mean_params(),
-                synthetic.make_regressor_state(seed=0), synthetic.make_gru_state(seed=0), write_mesh=not jo).cuda()
+                synthetic.make_regressor_state(seed=0), synthetic.make_gru_state(seed=0), write_mesh=not jo, joints_mode="skin").cuda()
 flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 256, 512, 1024]
 peak = json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").exists() else 6548.5
