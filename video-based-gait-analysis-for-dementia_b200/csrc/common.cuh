@@ -117,6 +117,6 @@ bool gru_small_eligible(const float* gi, const float* W_hh, const float* h0, con
                         int64_t H);
 int gru_small_launch(const float* gi, const float* W_hh, const float* b_hh, const float* h0, float* y, int64_t ldy,
                      const float* resid, int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T, int reverse,
-                     unsigned int* flags, cudaStream_t stream);
+                     void* exchange, cudaStream_t stream);
 
 }  // namespace gait

@@ -113,8 +113,8 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
         gru_small = (e && atoi(e) == 0) ? 0 : 1;
     }
     if (gru_path != 1 && gru_small && gru_small_eligible(gi, W_hh, h0, y, ldy, S, T, H) && T >= 4) {
-        unsigned int* flags = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);
-        const int rc = gru_small_launch(gi, W_hh, b_hh, h0, y, ldy, resid, ldres, out, ldout, hn, S, T, reverse, flags, st);
+        // the per-step path's partial-sum area (4 x S x 3H floats, unused here) holds the (value, tag) exchange buffer: 2 x S x H pairs
+        const int rc = gru_small_launch(gi, W_hh, b_hh, h0, y, ldy, resid, ldres, out, ldout, hn, S, T, reverse, gh, st);
         if (rc != GAIT_GRU_RETRY_PER_STEP) return rc;
     }
     if (gru_path != 1 && linear_path() != 1) {
