@@ -68,3 +68,45 @@ def test_gather_single_process_checks_counts():
     with pytest.raises(ValueError):
         gather_sequences(x, 5)
     assert max_over_ranks(3.5) == 3.5
+
+
+def test_root_gather_piece_bounds_cover_every_shard():
+    """RootGather cuts a rank's shard into sequence chunks x SMPL pieces; the root derives every OTHER rank's piece bounds from
+    the same rule (that is what its receive slices are built from).  The pieces must tile each shard exactly, for even and
+    ragged shards."""
+    from gaitb200.sharding import RootGather
+    for S_total, world, chunks, smpl in ((1024, 8, 2, 4), (1024, 2, 1, 8), (10, 2, 2, 1), (9, 2, 1, 3), (7, 3, 2, 2)):
+        chunks_eff = max(1, min(chunks, min(shard_counts(S_total, world))))
+        for r in range(world):
+            lo, hi = shard_bounds(S_total, world, r)
+            fake = type("F", (), {})()                           # only the two attributes _piece_bounds reads
+            fake.cb = [shard_bounds(hi - lo, chunks_eff, c) for c in range(chunks_eff)]
+            fake.smpl_chunks = smpl
+            pieces = RootGather._piece_bounds(fake, hi - lo)
+            assert pieces[0][0] == 0 and pieces[-1][1] == hi - lo
+            assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:])) and all(b > a for a, b in pieces)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours) runs on CPU only and prints one JSON line with the
+    contract's keys; at N > 1 only rank 0 prints and the workload is all of BASELINE configs[2] (here shrunk by --seqs-per-gpu)."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    env = dict(os.environ, WORLD_SIZE="2", RANK="0", LOCAL_RANK="0", OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--seqs-per-gpu", "2", "--frames", "4"], capture_output=True, text=True, timeout=300, env=env, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["gpu_launches"] == 0
+    assert line["config"]["global_frames_per_step"] == 2 * 2 * 4 and "configs[2]" in line["config"]["workload"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    env["RANK"] = "1"
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--seqs-per-gpu", "2", "--frames", "4"], capture_output=True, text=True, timeout=300, env=env, cwd=str(root))
+    assert r.returncode == 0 and r.stdout.strip() == ""
