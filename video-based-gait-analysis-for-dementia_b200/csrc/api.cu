@@ -1,5 +1,6 @@
 // Library-level entry points: version, error text, device check, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -32,6 +33,15 @@ int device_sm_count() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 1; }
     if (dev >= 0 && dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
     return sms;
+}
+
+int pdl_mask() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GAITB200_PDL");
+        on = e ? atoi(e) : 1;
+    }
+    return on;
 }
 
 }  // namespace gait

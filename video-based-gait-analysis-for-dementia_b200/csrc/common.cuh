@@ -68,6 +68,38 @@ struct PerDeviceOnce {
     void mark(int dev) { if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release); }
 };
 
+// Programmatic dependent launch.  A kernel launched through launch_pdl() may begin while its predecessor in the stream is
+// still draining: its CTAs become resident as SMs free up and run their prologue (barrier init, tensor-memory allocation,
+// descriptor prefetch), then block in pdl_wait() until the predecessor has completed and its writes are visible.  Rules kept
+// by every kernel launched this way: (1) ALL threads execute pdl_wait() before their first global-memory access (reads of
+// constants included: a constant may have been written by the kernel just before), so "this grid completed" still implies
+// "everything before it completed"; (2) pdl_trigger() right after it lets the successor be scheduled as soon as every CTA
+// of this grid is resident.  Both are no-ops for a normal launch.
+// GAITB200_PDL is a mask of the kernel kinds that are launched this way: 1 = tensor-core GEMM, 2 = skinning, 4 = the small
+// kernels (chain, joint assembly, split-K reductions).  Measured in CUDA-graph replays of the C2 step (scripts/
+// pdl_graph_check.py, profiles/r02za_pdl.md): mask 0 729.6 us, 1 720.0, 2 743.5, 4 732.9, 7 735.7 - blocks that wait next to
+// a running kernel slow it down (chain beside the blend GEMM +5 us, skinning after the blend GEMM +3..7 us), so only the
+// GEMM -> GEMM chains of the regressor keep it: the default is 1.
+int pdl_mask();                                          // api.cu: bit 0 GEMM, bit 1 skinning, bit 2 small kernels
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl_mask() & kind) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // internal (not exported) variants used by composite entry points
 int linear_launch(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* Cin, int64_t ldcin, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,

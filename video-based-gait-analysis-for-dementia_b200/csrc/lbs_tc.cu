@@ -286,6 +286,10 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
+    // programmatic dependent launch (common.cuh): the prologue above ran under the tail of the previous kernel (in a step: the
+    // blend GEMM, whose CTAs finish at different times); v_posed, the transform blobs and the weights are read after this
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == W_PROD_A) {
         // ---------------------------------------------------------------- transform-blob producer (one elected lane)
@@ -614,8 +618,8 @@ static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, co
     GAIT_TRY(make_tensor_map_2d(&tmV, 8, v_posed, (uint64_t)(V * 3 / 2), (uint64_t)F, (uint64_t)ldv * sizeof(float),
                                 lbs::VT * 3 / 2, lbs::FT, false));
 #define GAIT_LBS_LAUNCH(JX, MESH)                                                                                       \
-    lbs::smpl_lbs_tc_kernel<JX, MESH><<<grid, lbs::THREADS3, lbs::SMEM3, stream>>>(                                       \
-        tmV, Aop, Wpack, jx, verts, jx_partial, lm_idx, n_lm, lm_out, (int)F, (int)V, (int)groups, (int)tiles, (int)n_items)
+    launch_pdl(2, lbs::smpl_lbs_tc_kernel<JX, MESH>, dim3(grid), dim3(lbs::THREADS3), lbs::SMEM3, stream,                    \
+               tmV, Aop, Wpack, jx, verts, jx_partial, lm_idx, n_lm, lm_out, (int)F, (int)V, (int)groups, (int)tiles, (int)n_items)
     if (jx && mesh) GAIT_LBS_LAUNCH(true, true);
     else if (jx) GAIT_LBS_LAUNCH(true, false);
     else if (mesh) GAIT_LBS_LAUNCH(false, true);

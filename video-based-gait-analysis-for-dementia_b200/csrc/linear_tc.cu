@@ -244,6 +244,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail; nothing below may start before
+    // that kernel has completed.  The successor may be scheduled from here on (it needs this CTA's SM to become free anyway).
+    pdl_wait();
+    pdl_trigger();
 
     // Every role runs its own loop over the CTA's work items (it = k-blocks processed so far = position in the stage ring,
     // ch = accumulator chunks so far = position in the TMEM ring), so that the register budget can be re-divided per
@@ -574,9 +578,14 @@ static int launch(const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensor
         set_error("linear(tc): GAITB200_TC_DRAIN must be 1 or 2");
         return GAIT_ERR_INVALID;
     }
-    gemm_tf32x3_kernel<BN, QLO><<<grid, THREADS, cfg::SMEM, stream>>>(tmP, tmQ, tmQlo, bias, Cin, ldcin, C, ldc, P_rows, Q_rows, K,
-                                                                     transposed, kb_per_split, split_stride, tiles_p, splits,
-                                                                     n_items, mode, drain, g_trace);
+    cudaError_t le = launch_pdl(1, gemm_tf32x3_kernel<BN, QLO>, grid, dim3(THREADS), cfg::SMEM, stream, tmP, tmQ, tmQlo, bias, Cin, ldcin,
+                                C, ldc, P_rows, Q_rows, K, transposed, kb_per_split, split_stride, tiles_p, splits, n_items, mode,
+                                drain, g_trace);
+    if (le != cudaSuccess) {
+        cudaGetLastError();
+        set_error("linear(tf32x3 tcgen05): %s", cudaGetErrorString(le));
+        return GAIT_ERR_CUDA;
+    }
     return check_launch("linear(tf32x3 tcgen05)");
 }
 

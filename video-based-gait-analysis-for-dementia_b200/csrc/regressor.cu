@@ -18,6 +18,8 @@ constexpr int kStateLd = 160;
 
 __global__ void broadcast_state_kernel(const float* __restrict__ init, int64_t init_rows, float* __restrict__ state,
                                        int64_t F) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= F * kStateLd) return;
     const int64_t f = i / kStateLd;
@@ -33,6 +35,8 @@ __global__ void broadcast_state_kernel(const float* __restrict__ init, int64_t i
 __global__ void init_term_kernel(const float* __restrict__ W1s, const float* __restrict__ init, const float* __restrict__ b1,
                                  float* __restrict__ bias1, int64_t Dh, float* __restrict__ state, int64_t F,
                                  unsigned state_blocks) {
+    pdl_wait();
+    pdl_trigger();
     if (blockIdx.x < state_blocks) {
         const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
         if (i < F * kStateLd) {
@@ -59,6 +63,8 @@ constexpr int kDecSplits = 6;          // split-K of the 157-row decoder GEMM (o
 // state[f, c] += sum over split-K partials (partial 0 already holds bias); one thread per element
 __global__ void decoder_reduce_kernel(const float* __restrict__ part, int parts, int64_t part_stride,
                                       float* __restrict__ state, int64_t F) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= F * kStateLd) return;
     const int c = (int)(i % kStateLd);
@@ -71,6 +77,8 @@ __global__ void decoder_reduce_kernel(const float* __restrict__ part, int parts,
 // state[f, c] = sum over split-K partials (partial 0 holds the bias); padding columns are zeroed
 __global__ void folded_reduce_kernel(const float* __restrict__ part, int parts, int64_t part_stride,
                                      float* __restrict__ state, int64_t F) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= F * kStateLd) return;
     const int c = (int)(i % kStateLd);
@@ -123,7 +131,7 @@ int gait_hmr_regressor_folded(const float* x, int64_t ldx, const float* Wf, cons
     } else {
         GAIT_TRY(linear_launch(x, ldx, Wf, Din, bf, nullptr, 0, part, kStateLd, F, kState, Din, st));
     }
-    folded_reduce_kernel<<<(unsigned)ceil_div(F * kStateLd, 256), 256, 0, st>>>(part, splits, F * kStateLd, state_out, F);
+    launch_pdl(4, folded_reduce_kernel, dim3((unsigned)ceil_div(F * kStateLd, 256)), dim3(256), 0, st, part, splits, F * kStateLd, state_out, F);
     return check_launch("hmr folded_reduce");
 }
 
@@ -158,11 +166,11 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
     }
     const unsigned state_blocks = (unsigned)ceil_div(F * kStateLd, 256);
     if (shared_init && n_iter > 0) {
-        init_term_kernel<<<state_blocks + (unsigned)ceil_div(Dh * 32, 256), 256, 0, st>>>(W1s, init, b1, bias1, Dh, state_out,
-                                                                                             F, state_blocks);
+        launch_pdl(4, init_term_kernel, dim3(state_blocks + (unsigned)ceil_div(Dh * 32, 256)), dim3(256), 0, st, W1s, init, b1, bias1, Dh,
+                   state_out, F, state_blocks);
         GAIT_TRY(check_launch("hmr init_term + broadcast_state"));
     } else {
-        broadcast_state_kernel<<<state_blocks, 256, 0, st>>>(init, init_rows, state_out, F);
+        launch_pdl(4, broadcast_state_kernel, dim3(state_blocks), dim3(256), 0, st, init, init_rows, state_out, F);
         GAIT_TRY(check_launch("hmr broadcast_state"));
     }
     if (n_iter == 0) return GAIT_OK;
@@ -177,8 +185,8 @@ int gait_hmr_regressor(const float* x, int64_t ldx, const float* W1x, const floa
         if (dsplits > 1) {
             GAIT_TRY(linear_tc_launch(h2, Dh, Wd, Dh, bd, nullptr, 0, dpart, kStateLd, F, kState, Dh, dsplits,
                                       F * kStateLd, st));
-            decoder_reduce_kernel<<<(unsigned)ceil_div(F * kStateLd, 256), 256, 0, st>>>(dpart, dsplits, F * kStateLd,
-                                                                                           state_out, F);
+            launch_pdl(4, decoder_reduce_kernel, dim3((unsigned)ceil_div(F * kStateLd, 256)), dim3(256), 0, st, dpart, dsplits,
+                       F * kStateLd, state_out, F);
             GAIT_TRY(check_launch("hmr decoder_reduce"));
         } else {
             GAIT_TRY(linear_launch(h2, Dh, Wd, Dh, bd, state_out, kStateLd, state_out, kStateLd, F, kState, Dh, st));

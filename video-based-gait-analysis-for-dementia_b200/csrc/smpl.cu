@@ -32,6 +32,8 @@ smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ x6
                        float* __restrict__ coef, float* __restrict__ Aop, int64_t F) {
     __shared__ int s_parent[32];
     __shared__ int s_depth[32];
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 32) s_parent[threadIdx.x] = (threadIdx.x < NJ) ? parents[threadIdx.x] : -1;
     __syncthreads();
@@ -365,6 +367,8 @@ joints_assemble_kernel(const float* __restrict__ J_posed, const float* __restric
                        float divisor, float* __restrict__ kp2d, const int32_t* __restrict__ gather,
                        int n_gather, float* __restrict__ gathered, int64_t F) {
     __shared__ float ex_s[JA_FB][JA_MAX_EXTRA * 3];
+    pdl_wait();
+    pdl_trigger();
     const int64_t f0 = (int64_t)blockIdx.x * JA_FB;
     const int nf = (int)min((int64_t)JA_FB, F - f0);
     // phase 1: sum the partial extra joints; 8 consecutive lanes share one (frame, joint, coordinate)
@@ -446,6 +450,8 @@ __global__ void pack_theta_kernel(const float* __restrict__ R, const float* __re
 __global__ void smpl_reduced_joints_kernel(const float* __restrict__ A, const float* __restrict__ u, int64_t ldu,
                                            const float* __restrict__ lm_weights, const float* __restrict__ s,
                                            float* __restrict__ lm_out, float* __restrict__ thorax, int64_t F, int n_lm) {
+    pdl_wait();
+    pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int per = n_lm + 1;
     if (i >= F * per) return;
@@ -498,7 +504,7 @@ int gait_smpl_pose_chain(const float* R, const float* betas, int64_t ldb, const 
     GAIT_REQUIRE(R && betas && J_template && J_shapedirs && parents && J_posed && (A || Aop), "smpl_pose_chain: null pointer");
     GAIT_REQUIRE(ldb >= NB, "smpl_pose_chain: ldb < 10");
     GAIT_REQUIRE(A == nullptr || aligned16(A), "smpl_pose_chain: A must be 16-byte aligned");
-    smpl_pose_chain_kernel<<<(unsigned)ceil_div(F, kChainWarps), kChainWarps * 32, 0, as_stream(stream)>>>(
+    launch_pdl(4, smpl_pose_chain_kernel, dim3((unsigned)ceil_div(F, kChainWarps)), dim3(kChainWarps * 32), 0, as_stream(stream),
         R, nullptr, 0, 0.f, nullptr, betas, ldb, nullptr, 0, nullptr, J_template, J_shapedirs, parents, A, J_posed, coef, Aop, F);
     return check_launch("smpl_pose_chain");
 }
@@ -514,7 +520,7 @@ int gait_smpl_pose_chain_rot6d(const float* x6, int64_t ldx6, float eps, const f
     GAIT_REQUIRE(ldx6 >= 6 * NJ && (ldx6 & 1) == 0 && aligned8(x6) && ldb >= NB, "smpl_pose_chain_rot6d: bad stride or alignment");
     GAIT_REQUIRE(theta == nullptr || (cam && ldcam >= 3), "smpl_pose_chain_rot6d: theta needs cam");
     GAIT_REQUIRE(A == nullptr || aligned16(A), "smpl_pose_chain_rot6d: A must be 16-byte aligned");
-    smpl_pose_chain_kernel<<<(unsigned)ceil_div(F, kChainWarps), kChainWarps * 32, 0, as_stream(stream)>>>(
+    launch_pdl(4, smpl_pose_chain_kernel, dim3((unsigned)ceil_div(F, kChainWarps)), dim3(kChainWarps * 32), 0, as_stream(stream),
         nullptr, x6, ldx6, eps, R_out, betas, ldb, cam, ldcam, theta, J_template, J_shapedirs, parents, A, J_posed, coef, Aop, F);
     return check_launch("smpl_pose_chain_rot6d");
 }
@@ -565,7 +571,7 @@ int gait_joints_assemble(const float* J_posed, const float* verts, int64_t V, co
     GAIT_REQUIRE(kp2d == nullptr || (cam && ldcam >= 3 && aligned8(kp2d)), "joints_assemble: kp2d needs cam");
     GAIT_REQUIRE(n_gather == 0 || (gather && gathered), "joints_assemble: gather needs output");
     GAIT_REQUIRE(n_extra <= JA_MAX_EXTRA, "joints_assemble: at most 9 extra joints");
-    joints_assemble_kernel<<<(unsigned)ceil_div(F, JA_FB), 256, 0, as_stream(stream)>>>(
+    launch_pdl(4, joints_assemble_kernel, dim3((unsigned)ceil_div(F, JA_FB)), dim3(256), 0, as_stream(stream),
         J_posed, verts, V, landmarks, n_landmarks, ExtraJoints{extra, n_extra, extra_parts, extra_part_stride}, joint_map, J,
         joints, cam, ldcam, focal_length,
         img_res, kp2d_divisor, kp2d, gather, n_gather, gathered, F);
@@ -588,7 +594,8 @@ int gait_smpl_reduced_joints(const float* A, const float* u, int64_t ldu, const 
     GAIT_REQUIRE(A && u && lm_weights && s && lm_out && thorax, "smpl_reduced_joints: null pointer");
     GAIT_REQUIRE(ldu >= 3 * n_lm + 3 * GAIT_NUM_JOINTS, "smpl_reduced_joints: ldu < 3 n_lm + 72");
     const int64_t n = F * (n_lm + 1);
-    smpl_reduced_joints_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(A, u, ldu, lm_weights, s, lm_out, thorax, F, n_lm);
+    launch_pdl(4, smpl_reduced_joints_kernel, dim3((unsigned)ceil_div(n, 128)), dim3(128), 0, as_stream(stream), A, u, ldu, lm_weights, s,
+               lm_out, thorax, F, n_lm);
     return check_launch("smpl_reduced_joints");
 }
 
