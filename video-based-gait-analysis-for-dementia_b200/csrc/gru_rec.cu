@@ -61,7 +61,16 @@ constexpr int DRAIN_KB = 2;                 // k-blocks per promotion
 constexpr int NGRP = 2;                     // converter groups of 4 warps alternating k-blocks (a third group: 768 threads with
                                             // setmaxnreg, 0.475 vs 0.483 ms - not kept; it would also need its own barrier split)
 constexpr int NPROM = 256, NCONV = 128 * NGRP;
-constexpr int THREADS = 128 + NPROM + NCONV;
+#ifndef GRU_ACOPY
+#define GRU_ACOPY 1                         // 1: the A operand goes shared -> tensor memory by tcgen05.cp (warp 20); 0: through the converters' registers
+#endif
+constexpr int THREADS = 128 + NPROM + NCONV + (GRU_ACOPY ? 32 : 0);
+// Register budget (setmaxnreg, one instruction per warpgroup).  The promotion warps hold a 128 x 48 FP32 tile, four gate
+// operands and the previous h per thread; the other roles are small.  setmaxnreg.inc blocks until the CTA's pool (THREADS x
+// the kernel's register count R) holds the registers, so the launcher checks R against this budget (regs_ok) instead of
+// trusting the compiler: 128 x 40 + 256 x 120 + 256 x 56 + 32 x R <= 672 x R  <=>  R >= 80.
+constexpr int REGS_WG0 = 40, REGS_PROM = 120, REGS_CONV = 56;
+constexpr int REGS_MIN_KERNEL = GRU_ACOPY ? (128 * REGS_WG0 + NPROM * REGS_PROM + NCONV * REGS_CONV + 639) / 640 : 0;
 constexpr int OFF_P = STAGES * STAGE;
 constexpr int OFF_BAR = OFF_P + P_FLOATS * 4;       // one partial-sum buffer (P_FREE handshake before it is rewritten)
 constexpr int BAR_AREA = 384;               // barriers (8 B each) + the TMEM base slot in the last 8 bytes
@@ -93,6 +102,15 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared memory -> tensor memory copy of a 128-row x 256-bit tile (8 FP32 columns per lane), source given by a UMMA
+// shared-memory matrix descriptor; asynchronous, tracked by the tcgen05.commit the same thread issues after it
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // debug timestamps of CTA 0: trace[step*8 + i] (step < 32) and trace[256 + kb*8 + i] for the k-blocks of step 2
@@ -130,7 +148,7 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 mbar_init(BAR(B_FULL_W + s + j * STAGES), 3);       // one 32-row box per gate, each issued by its own lane
                 mbar_init(BAR(B_FULL_H + s + j * STAGES), 4);       // h and h_lo, two 32-sequence boxes each
             }
-            mbar_init(BAR(B_CONV + s), 4);                // one arrival per warp of the converter group that owns the k-block
+            mbar_init(BAR(B_CONV + s), 4 + GRU_ACOPY);    // one arrival per warp of the converter group that owns the k-block (+ the A copy's commit)
             mbar_init(BAR(B_EMPTY + s), 1);
         }
         for (int b = 0; b < NBUF; ++b) {
@@ -151,6 +169,11 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
     cluster_sync_all();                                // peers' barriers exist before anyone arrives on them remotely
     const uint32_t tmem_d = *tmem_slot;
 
+    if (warp < 4) {
+    // one setmaxnreg per warpgroup (all four warps execute the same instruction); the roles branch below it
+#if GRU_ACOPY
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_WG0));
+#endif
     if (warp == 0) {
         // ------------------------------------------------------------ W_hh tile producer (independent of h)
         // TMA issue laws measured on this machine (scripts/microbench/kblock_pipe.cu, tma_issue.cu): a TMA warp
@@ -167,8 +190,15 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                     mbar_wait(BAR(B_EMPTY + s), ph ^ 1);
                     if (g == 0) GRU_TRACE_KB(0);
                     const uint32_t fb = BAR(B_FULL_W + full_slot(my));
+#ifdef GRU_EXP_WBULK   // timing experiment only (wrong results): the W tile of a k-block as ONE contiguous 12 KB bulk copy
+                    if (g == 0) {
+                        mbar_arrive_expect_tx(fb, W_TILE);
+                        bulk_g2s(base + s * STAGE + A_TILE, gi + (((size_t)blockIdx.x * NKB + kb) % 2000) * (W_TILE / 4), W_TILE, fb);
+                    } else mbar_arrive(fb);
+#else
                     mbar_arrive_expect_tx(fb, G_TILE);
                     tma_load_2d(base + s * STAGE + A_TILE + g * G_TILE, &tmW, k0 + kb * BK, g * H + u0, fb);
+#endif
                 }
                 __syncwarp();
                 it += min(2, NKB - kb0);
@@ -216,15 +246,19 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                     const uint32_t fb = BAR(B_FULL_H + full_slot(my));
                     mbar_arrive_expect_tx(fb, H_TILE / 2);
                     const uint32_t dst = base + s * STAGE + part * H_TILE + half * (H_TILE / 2);
+#ifdef GRU_EXP_HBULK   // timing experiment only (wrong results): every 32-sequence h box as one contiguous 4 KB bulk copy
+                    bulk_g2s(dst, y + ((size_t)(tp < 0 ? 0 : tp) * NKB * 4 + kb * 4 + (lane & 3)) * (H_TILE / 8), H_TILE / 2, fb);
+#else
                     if (part) tma_load_3d(dst, &tmL, k0 + kb * BK, lslot, half * (SB / 2), fb);
                     else if (step == 0) tma_load_3d(dst, &tmH0, k0 + kb * BK, 0, half * (SB / 2), fb);
                     else tma_load_3d(dst, &tmY, k0 + kb * BK, tp, half * (SB / 2), fb);
+#endif
                 }
                 __syncwarp();
                 it += min(2, NKB - kb0);
             }
         }
-    } else if (warp == 1 || warp == 3) {
+    } else {
         // ------------------------------------------------------------ MMA issuers (warp-uniform, one lane issues)
         // Every warp-specialised role used to touch every k-block, so the k-block period was bounded below by the serial
         // latency chain of ONE warp's loop body (barrier probe -> issue -> commit, ~900 cycles), not by any throughput.
@@ -255,7 +289,9 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);
                         umma_tf32_ts(acc, a + 8 * k, b_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+#ifndef GRU_EXP_HALFMMA   // timing experiment only (wrong results): W_hi products only
                         umma_tf32_ts(acc, a + 8 * k, b_lo + adv, idesc, 1u);
+#endif
                     }
                     umma_commit(BAR(B_EMPTY + s));
                     if (last_of_chunk) umma_commit(BAR(B_ACC_FULL + buf));
@@ -266,7 +302,11 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
             }
             ch += nchunks;
         }
+    }
     } else if (warp >= 12 && warp < 20) {
+#if GRU_ACOPY
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONV));
+#endif
         // ------------------------------------------------------------ converters: two groups of 4 warps alternate k-blocks
         // W: lo tile only (the raw tile is the hi operand).  A: each thread moves one row of the stage's [h ; h_lo] tile
         // from shared memory into tensor memory (no arithmetic; TMEM lane = row, so a group needs all four warp quadrants).
@@ -284,12 +324,17 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 constexpr int NW = W_TILE / 16 / 128;                 // 6
                 mbar_wait(BAR(B_FULL_W + full_slot(it)), full_parity(it));
                 if (gt == 0) GRU_TRACE_KB(4);
+#ifndef GRU_EXP_NOWCONV   // timing experiment only (wrong results): no W_lo conversion (24 KB less shared-memory traffic per k-block)
                 float4 v[NW];
 #pragma unroll
                 for (int i = 0; i < NW; ++i) v[i] = w_hi[i * 128];
 #pragma unroll
                 for (int i = 0; i < NW; ++i)
                     w_lo[i * 128] = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+#else
+                (void)w_hi; (void)w_lo;
+#endif
+#if !GRU_ACOPY
                 mbar_wait(BAR(B_FULL_H + full_slot(it)), full_parity(it));
                 if (gt == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
                 {
@@ -307,13 +352,39 @@ gru_recurrent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
                 }
                 tmem_st_wait();
                 tc_fence_before();
+#endif
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(B_CONV + s));
                 if (gt == 0) GRU_TRACE_KB(6);
             }
         }
+    } else if (GRU_ACOPY && warp == 20) {
+        // ------------------------------------------------------------ A operand: [h ; h_lo] tile, shared -> tensor memory
+        // One thread hands the stage's 128 x 32 tile to the tensor core's copy engine (no LSU / ALU work, no register pass)
+        // and commits to the stage's "converted" barrier, next to the W_lo arrivals of the converter group.  The tensor-memory
+        // slot is free: its previous readers (the MMAs of k-block it - STAGES) retired before the stage was refilled.
+        int it = 0;
+        for (int step = first_gemm; step < T; ++step) {
+            for (int kb = 0; kb < NKB; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(BAR(B_FULL_H + full_slot(it)), full_parity(it));
+                if (lane == 0) { GRU_TRACE_KB(5); if (kb == 0) GRU_TRACE_STEP(1); }
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a_src = make_sdesc_sw128(base + s * STAGE);
+                    const uint32_t a = tmem_d + (uint32_t)(TMEM_A + s * BK);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) tmem_cp_128x256b(a + 8 * k, a_src + (uint64_t)(k * 32 >> 4));
+                    umma_commit(BAR(B_CONV + s));
+                }
+                __syncwarp();
+            }
+        }
     } else if (warp >= 4 && warp < 12) {
+#if GRU_ACOPY
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROM));
+#endif
         // ------------------------------------------------------------ promotion + gates
         const int pt = threadIdx.x - 128;
         const int q = warp & 3;                            // TMEM lane quadrant of this warp
@@ -481,6 +552,15 @@ static int max_coresident_ctas() {
         cudaOccupancyMaxActiveClusters(&n_clusters, gru_recurrent_kernel<false>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         n_clusters = 0;
+    }
+    if (REGS_MIN_KERNEL > 0) {   // the register pool must cover the setmaxnreg budget, or the promotion warps would wait forever
+        cudaFuncAttributes fa0, fa1;
+        if (cudaFuncGetAttributes(&fa0, gru_recurrent_kernel<false>) != cudaSuccess ||
+            cudaFuncGetAttributes(&fa1, gru_recurrent_kernel<true>) != cudaSuccess || fa0.numRegs < REGS_MIN_KERNEL ||
+            fa1.numRegs < REGS_MIN_KERNEL) {
+            cudaGetLastError();
+            n_clusters = 0;
+        }
     }
     if (dev >= 0 && dev < 64) cache[dev].store(n_clusters * KG + 1, std::memory_order_relaxed);
     return n_clusters * KG;
