@@ -128,6 +128,11 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
                    int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T, int64_t I,
                    int64_t H, int reverse, void* workspace, size_t workspace_bytes, gait_stream_t stream);
 
+/* Which recurrence implementation gait_gru_layer uses for (S,T,H) on the current device with 16-byte aligned operands and
+ * H-wide strides: 2 = weight-stationary kernel (1-2 sequences), 1 = persistent cluster kernel (64-sequence launches),
+ * 0 = one GEMM + gate kernel per time step.  Needs a device (queries occupancy and the kernels' register counts). */
+int gait_gru_plan(int64_t S, int64_t T, int64_t H);
+
 /* Debug hook: device buffer of 1280 uint64 receiving clock64 stamps of CTA 0 of the persistent recurrent kernel
  * (per step: [step*8+i]; per k-block of step 2: [256+kb*8+i]); NULL disables. */
 int gait_debug_gru_trace(unsigned long long* device_buffer);

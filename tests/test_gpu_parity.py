@@ -193,6 +193,20 @@ def test_gru_layer_h0_hn_residual(S, T, H, reverse, lib_loaded):
     assert maxerr(hn, hn_ref[0]) <= 2e-5
 
 
+def test_gru_plan_selects_the_fast_kernels(lib_loaded):
+    """The shapes the bench times must get the kernels DESIGN.md describes; a build whose persistent kernel fell back to the
+    per-step path (co-residency or setmaxnreg register budget not met) fails here instead of just running slower."""
+    import os
+    if any(os.environ.get(k) for k in ("GAITB200_GRU_PATH", "GAITB200_GRU_SMALL", "GAITB200_GRU_MAXCHUNKED", "GAITB200_LINEAR")):
+        pytest.skip("GRU path overridden by the environment")
+    plan = lib_loaded.load().gait_gru_plan
+    assert plan(64, 16, 2048) == 1          # C2: persistent cluster kernel
+    assert plan(128, 16, 2048) == 1         # C3 at 8 GPUs: two 64-sequence launches
+    assert plan(1, 900, 2048) == 2          # C4: weight-stationary kernel
+    assert plan(1024, 16, 2048) == 0        # C3 on one GPU: per-step GEMMs
+    assert plan(4, 6, 300) == 0             # H not a multiple of 64
+
+
 def test_temporal_encoder_variants(lib_loaded):
     from gaitb200.temporal import TemporalEncoder
     from oracle.temporal import TemporalEncoder as OT

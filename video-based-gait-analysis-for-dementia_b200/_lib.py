@@ -41,6 +41,7 @@ _SIGS = {
     "gait_debug_linear_trace": [P],
     "gait_debug_gru_trace": [P],
     "gait_gru_workspace_bytes": [I64, I64, I64],
+    "gait_gru_plan": [I64, I64, I64],
     "gait_gru_layer": [P, I64, P, P, P, P, P, P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I32, P, SZ, P],
     "gait_relu": [P, P, I64, P],
     "gait_hmr_workspace_bytes": [I64, I64],

@@ -72,6 +72,19 @@ size_t gait_gru_workspace_bytes(int64_t S, int64_t T, int64_t H) {
            + (size_t)(2 * S * H) * sizeof(float);   // + per-CTA step flags (one 128-byte line each) and the h_lo scratch of the persistent kernel
 }
 
+int gait_gru_plan(int64_t S, int64_t T, int64_t H) {
+    if (S <= 0 || T <= 0 || H <= 0) return 0;
+    const char* e = getenv("GAITB200_GRU_PATH");
+    if ((e && atoi(e) == 1) || linear_path() == 1) return 0;
+    const float* a = reinterpret_cast<const float*>(uintptr_t(256));        // stands for any 16-byte aligned operand
+    const char* sm = getenv("GAITB200_GRU_SMALL");
+    if (!(sm && atoi(sm) == 0) && T >= 4 && gru_small_eligible(a, a, nullptr, a, H, S, T, H)) return 2;
+    const char* mc = getenv("GAITB200_GRU_MAXCHUNKED");
+    const int64_t max_chunked = mc ? atoll(mc) : 320;
+    if (S <= max_chunked && gru_recurrent_eligible(a, a, nullptr, a, H, a, H, a, H, std::min<int64_t>(S, 64), T, H)) return 1;
+    return 0;
+}
+
 int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* W_hh, const float* b_ih,
                    const float* b_hh, const float* h0, float* y, int64_t ldy, const float* resid,
                    int64_t ldres, float* out, int64_t ldout, float* hn, int64_t S, int64_t T, int64_t I,

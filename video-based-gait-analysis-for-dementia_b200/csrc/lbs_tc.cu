@@ -291,6 +291,15 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     pdl_wait();
     pdl_trigger();
 
+#ifndef GAIT_LBS_REGS_CONSUMER
+#define GAIT_LBS_REGS_CONSUMER 128          // 0: no setmaxnreg (every warp keeps the kernel's 96 registers)
+#endif
+    if (warp >= W_PROD_A && warp < W_LOADER) {
+    // one setmaxnreg per warpgroup (all four warps must execute the same instruction): the producers and the MMA issuer are
+    // small; what they give up lets a consumer thread keep its 96 accumulator columns and 24 v_posed values in registers
+#if GAIT_LBS_REGS_CONSUMER
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+#endif
     if (warp == W_PROD_A) {
         // ---------------------------------------------------------------- transform-blob producer (one elected lane)
         ItemCursor c = cur0;
@@ -328,38 +337,6 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
                 }
             }
             __syncwarp();
-        }
-    } else if (warp >= W_LOADER) {
-        // ---------------------------------------------------------------- weight loader: vertex tile -> tensor memory
-        // The skinning weights are the M-side operand of every MMA of a vertex tile (~46 work items per CTA), so
-        // they live in tensor memory (lane = vertex, columns [hi 24 | lo 24]) instead of being re-read from shared
-        // memory by each of the 9 MMAs of each item.  Two buffers: the next tile is loaded while the current one is used.
-        const int row = (warp & 3) * 32 + lane;                    // TMEM lane = vertex within the tile
-        ItemCursor c = cur0;
-        int cur_tile = -1, i = -1;
-        for (int n = 0; n < item_hi - item_lo; ++n, c.next()) {
-            if (c.tile == cur_tile) continue;          // same rule as the MMA issuer: one load per run of items of a tile
-            cur_tile = c.tile;
-            ++i;
-            const int tile = c.tile;
-            const int b = i & 1;
-            if (i >= 2) mbar_wait(WFREE(b), ((i >> 1) - 1) & 1);
-            const float* blob = Wpack + (int64_t)tile * (W_BLOB / 4);
-            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(TMEM_W + b * W_COLS);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-#pragma unroll
-                for (int c = 0; c < NJ / 8; ++c) {
-                    float v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = blob[part * (W_PART / 4) + blob_index(VT, row, c * 8 + k)];
-                    tmem_st8(ta + part * NJ + c * 8, v);
-                }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(WFULL(b));
         }
     } else if (warp == W_MMA) {
         // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one lane issues)
@@ -405,7 +382,46 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
             __syncwarp();
             c = nx;
         }
+    }
+    } else if (warp >= W_LOADER) {
+#if GAIT_LBS_REGS_CONSUMER
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+#endif
+        // ---------------------------------------------------------------- weight loader: vertex tile -> tensor memory
+        // The skinning weights are the M-side operand of every MMA of a vertex tile (~46 work items per CTA), so
+        // they live in tensor memory (lane = vertex, columns [hi 24 | lo 24]) instead of being re-read from shared
+        // memory by each of the 9 MMAs of each item.  Two buffers: the next tile is loaded while the current one is used.
+        const int row = (warp & 3) * 32 + lane;                    // TMEM lane = vertex within the tile
+        ItemCursor c = cur0;
+        int cur_tile = -1, i = -1;
+        for (int n = 0; n < item_hi - item_lo; ++n, c.next()) {
+            if (c.tile == cur_tile) continue;          // same rule as the MMA issuer: one load per run of items of a tile
+            cur_tile = c.tile;
+            ++i;
+            const int tile = c.tile;
+            const int b = i & 1;
+            if (i >= 2) mbar_wait(WFREE(b), ((i >> 1) - 1) & 1);
+            const float* blob = Wpack + (int64_t)tile * (W_BLOB / 4);
+            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(TMEM_W + b * W_COLS);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+#pragma unroll
+                for (int c = 0; c < NJ / 8; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = blob[part * (W_PART / 4) + blob_index(VT, row, c * 8 + k)];
+                    tmem_st8(ta + part * NJ + c * 8, v);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(WFULL(b));
+        }
     } else if (warp < NCOMPUTE / 32) {
+#if GAIT_LBS_REGS_CONSUMER
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GAIT_LBS_REGS_CONSUMER));
+#endif
         // ---------------------------------------------------------------- consumer groups
         // Thread = vertex (TMEM lane).  Everything an item needs is pulled into registers at once - the 96 accumulator
         // columns (T for 8 frames) and the vertex's 8 v_posed entries - after which the accumulator and the v_posed slot
@@ -605,6 +621,17 @@ static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, co
         GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
         GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
         GAIT_CUDA(cudaFuncSetAttribute(lbs::smpl_lbs_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lbs::SMEM3));
+#if GAIT_LBS_REGS_CONSUMER
+        // setmaxnreg.inc waits until the CTA's register pool (threads x the kernel's register count) can supply the consumers'
+        // budget; a build whose register count came out lower would hang, so refuse it here
+        cudaFuncAttributes fa;
+        GAIT_CUDA(cudaFuncGetAttributes(&fa, lbs::smpl_lbs_tc_kernel<true, true>));
+        if ((int64_t)fa.numRegs * lbs::THREADS3 < (int64_t)lbs::NCOMPUTE * GAIT_LBS_REGS_CONSUMER + (lbs::THREADS3 - lbs::NCOMPUTE) * 48) {
+            set_error("smpl_lbs_tc: kernel compiled to %d registers, the setmaxnreg budget needs %d", fa.numRegs,
+                      (int)((lbs::NCOMPUTE * GAIT_LBS_REGS_CONSUMER + (lbs::THREADS3 - lbs::NCOMPUTE) * 48) / lbs::THREADS3));
+            return GAIT_ERR_UNSUPPORTED;
+        }
+#endif
         attr_once.mark(dev);
     }
     const int n_sms = device_sm_count();
