@@ -159,7 +159,10 @@ __global__ void lbs_pack_weights_kernel(const float* __restrict__ W, float* __re
 constexpr int NA = GAIT_LBS_NA;                          // transform-blob stages (L2 latency)
 constexpr int NV = GAIT_LBS_NV;                          // v_posed stages (HBM latency); a slot is released as soon as its rows are in registers
 constexpr int NACC = 4;                                  // TMEM accumulator buffers (4 x 96 = 384 columns)
-constexpr int NG = 3;                                    // consumer groups
+#ifndef GAIT_LBS_NG
+#define GAIT_LBS_NG 3
+#endif
+constexpr int NG = GAIT_LBS_NG;                          // consumer groups
 static_assert(NV % NG == 0, "a consumer group must meet every phase of the v_posed barriers it waits on");
 constexpr int V_STAGE = FT * V_ROW;                      // 12 288 B
 constexpr int OFF_A = 0;
@@ -292,13 +295,14 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     pdl_trigger();
 
 #ifndef GAIT_LBS_REGS_CONSUMER
-#define GAIT_LBS_REGS_CONSUMER 128          // 0: no setmaxnreg (every warp keeps the kernel's 96 registers)
+#define GAIT_LBS_REGS_CONSUMER (GAIT_LBS_NG == 4 ? 96 : 128)   // 0: no setmaxnreg (every warp keeps the kernel's registers)
 #endif
+#define GAIT_LBS_REGS_OTHER (GAIT_LBS_NG == 4 ? 40 : 48)
     if (warp >= W_PROD_A && warp < W_LOADER) {
     // one setmaxnreg per warpgroup (all four warps must execute the same instruction): the producers and the MMA issuer are
     // small; what they give up lets a consumer thread keep its 96 accumulator columns and 24 v_posed values in registers
 #if GAIT_LBS_REGS_CONSUMER
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GAIT_LBS_REGS_OTHER));
 #endif
     if (warp == W_PROD_A) {
         // ---------------------------------------------------------------- transform-blob producer (one elected lane)
@@ -385,7 +389,7 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     }
     } else if (warp >= W_LOADER) {
 #if GAIT_LBS_REGS_CONSUMER
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(48));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GAIT_LBS_REGS_OTHER));
 #endif
         // ---------------------------------------------------------------- weight loader: vertex tile -> tensor memory
         // The skinning weights are the M-side operand of every MMA of a vertex tile (~46 work items per CTA), so
@@ -626,9 +630,9 @@ static int lbs_tc_launch(const float* v_posed, int64_t ldv, const float* Aop, co
         // budget; a build whose register count came out lower would hang, so refuse it here
         cudaFuncAttributes fa;
         GAIT_CUDA(cudaFuncGetAttributes(&fa, lbs::smpl_lbs_tc_kernel<true, true>));
-        if ((int64_t)fa.numRegs * lbs::THREADS3 < (int64_t)lbs::NCOMPUTE * GAIT_LBS_REGS_CONSUMER + (lbs::THREADS3 - lbs::NCOMPUTE) * 48) {
+        if ((int64_t)fa.numRegs * lbs::THREADS3 < (int64_t)lbs::NCOMPUTE * GAIT_LBS_REGS_CONSUMER + (lbs::THREADS3 - lbs::NCOMPUTE) * GAIT_LBS_REGS_OTHER) {
             set_error("smpl_lbs_tc: kernel compiled to %d registers, the setmaxnreg budget needs %d", fa.numRegs,
-                      (int)((lbs::NCOMPUTE * GAIT_LBS_REGS_CONSUMER + (lbs::THREADS3 - lbs::NCOMPUTE) * 48) / lbs::THREADS3));
+                      (int)((lbs::NCOMPUTE * GAIT_LBS_REGS_CONSUMER + (lbs::THREADS3 - lbs::NCOMPUTE) * GAIT_LBS_REGS_OTHER) / lbs::THREADS3));
             return GAIT_ERR_UNSUPPORTED;
         }
 #endif
