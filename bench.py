@@ -599,7 +599,7 @@ def run_single(args, local_rank: int):
                                 / (ms_per_step * 1e-3) / 1e9) / peaks["hbm_gbs"],
         "wall_s_timed_region": t_wall,
         "step_ms_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
-        "library": str(_lib.LIB_PATH.relative_to(ROOT)),
+        "library": os.path.relpath(str(_lib.LIB_PATH), str(ROOT)),
     }
     print(json.dumps(line), flush=True)
 
@@ -735,7 +735,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         "cpu_baseline": None,
         "wall_s_timed_region": t_wall,
         "step_ms_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
-        "library": str(_lib.LIB_PATH.relative_to(ROOT)),
+        "library": os.path.relpath(str(_lib.LIB_PATH), str(ROOT)),
     }
     print(json.dumps(line), flush=True)
 

@@ -13,7 +13,7 @@ from pathlib import Path
 import torch
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = Path(os.environ.get("GAITB200_LIB", _HERE / "lib" / "libgaitb200.so"))
+LIB_PATH = Path(os.environ.get("GAITB200_LIB", _HERE / "lib" / "libgaitb200.so")).resolve()
 
 P, I32, I64, F32, F64, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
