@@ -61,6 +61,13 @@ def time_graph(g, reps, n=30):
 
 out = {"pdl": os.environ.get("GAITB200_PDL", "1")}
 os.makedirs("gpurun_out", exist_ok=True)
+if os.environ.get("PDL_CHECK_QUICK") == "1":
+    g = graph_of([stages[n] for n in ("pose_chain", "blend", "lbs", "joints")], 4)
+    out["smpl_part_us_x4"] = round(time_graph(g, 4) * 1e3, 2)
+    g = graph_of([f for _, f in head._stages(p)], 1)
+    out["step_us"] = [round(time_graph(g, 1, n=60) * 1e3, 2) for _ in range(3)]
+    print(json.dumps(out), flush=True)
+    sys.exit(0)
 g = graph_of([stages["regressor"]], 8)
 out["regressor_us_x8"] = round(time_graph(g, 8) * 1e3, 2)
 g = graph_of([stages[n] for n in ("pose_chain", "blend", "lbs", "joints")], 4)

@@ -39,7 +39,7 @@ int pdl_mask() {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("GAITB200_PDL");
-        on = e ? atoi(e) : 1;
+        on = e ? atoi(e) : 3;
     }
     return on;
 }

@@ -77,12 +77,26 @@ struct PerDeviceOnce {
 // of this grid is resident.  Both are no-ops for a normal launch.
 // GAITB200_PDL is a mask of the kernel kinds that are launched this way: 1 = tensor-core GEMM, 2 = skinning, 4 = the small
 // kernels (chain, joint assembly, split-K reductions).  Measured in CUDA-graph replays of the C2 step (scripts/
-// pdl_graph_check.py, profiles/r02za_pdl.md): mask 0 729.6 us, 1 720.0, 2 743.5, 4 732.9, 7 735.7 - blocks that wait next to
-// a running kernel slow it down (chain beside the blend GEMM +5 us, skinning after the blend GEMM +3..7 us), so only the
-// GEMM -> GEMM chains of the regressor keep it: the default is 1.
+// pdl_graph_check.py, profiles/r02za_pdl.md).  With every thread in griddepcontrol.wait: mask 0 729.6 us, 1 720.0, 2 743.5,
+// 7 735.7 - CTAs that wait next to a running kernel slow it down.  With ONE waiting thread per CTA (pdl_wait_cta below; the
+// others sit at the CTA barrier) the skinning kernel gains too: mask 1 700.7 us, 3 696.3, 5 704.2, 7 708.0 (after the other
+// late changes).  The small kernels still lose, so the default is 3.
 int pdl_mask();                                          // api.cu: bit 0 GEMM, bit 1 skinning, bit 2 small kernels
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// variant for kernels whose CTAs may sit next to a running kernel: ONE thread blocks in griddepcontrol.wait, the others at a
+// CTA barrier (GAIT_PDL_WAIT_ONE=0 restores the all-threads wait)
+#ifndef GAIT_PDL_WAIT_ONE
+#define GAIT_PDL_WAIT_ONE 1
+#endif
+__device__ __forceinline__ void pdl_wait_cta() {
+#if GAIT_PDL_WAIT_ONE
+    if (threadIdx.x == 0) pdl_wait();
+    __syncthreads();
+#else
+    pdl_wait();
+#endif
+}
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {

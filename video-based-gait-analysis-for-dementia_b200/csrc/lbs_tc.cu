@@ -291,7 +291,7 @@ smpl_lbs_tc_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restr
     const uint32_t tmem_d = *tmem_slot;
     // programmatic dependent launch (common.cuh): the prologue above ran under the tail of the previous kernel (in a step: the
     // blend GEMM, whose CTAs finish at different times); v_posed, the transform blobs and the weights are read after this
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
 
 #ifndef GAIT_LBS_REGS_CONSUMER

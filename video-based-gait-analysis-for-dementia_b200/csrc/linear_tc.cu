@@ -246,7 +246,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     const uint32_t tmem_d = *tmem_slot;
     // programmatic dependent launch: everything above overlapped the previous kernel's tail; nothing below may start before
     // that kernel has completed.  The successor may be scheduled from here on (it needs this CTA's SM to become free anyway).
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
 
     // Every role runs its own loop over the CTA's work items (it = k-blocks processed so far = position in the stage ring,

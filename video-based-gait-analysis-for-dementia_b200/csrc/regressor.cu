@@ -18,7 +18,7 @@ constexpr int kStateLd = 160;
 
 __global__ void broadcast_state_kernel(const float* __restrict__ init, int64_t init_rows, float* __restrict__ state,
                                        int64_t F) {
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= F * kStateLd) return;
@@ -35,7 +35,7 @@ __global__ void broadcast_state_kernel(const float* __restrict__ init, int64_t i
 __global__ void init_term_kernel(const float* __restrict__ W1s, const float* __restrict__ init, const float* __restrict__ b1,
                                  float* __restrict__ bias1, int64_t Dh, float* __restrict__ state, int64_t F,
                                  unsigned state_blocks) {
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
     if (blockIdx.x < state_blocks) {
         const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -63,7 +63,7 @@ constexpr int kDecSplits = 6;          // split-K of the 157-row decoder GEMM (o
 // state[f, c] += sum over split-K partials (partial 0 already holds bias); one thread per element
 __global__ void decoder_reduce_kernel(const float* __restrict__ part, int parts, int64_t part_stride,
                                       float* __restrict__ state, int64_t F) {
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= F * kStateLd) return;
@@ -77,7 +77,7 @@ __global__ void decoder_reduce_kernel(const float* __restrict__ part, int parts,
 // state[f, c] = sum over split-K partials (partial 0 holds the bias); padding columns are zeroed
 __global__ void folded_reduce_kernel(const float* __restrict__ part, int parts, int64_t part_stride,
                                      float* __restrict__ state, int64_t F) {
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= F * kStateLd) return;

@@ -32,7 +32,7 @@ smpl_pose_chain_kernel(const float* __restrict__ R, const float* __restrict__ x6
                        float* __restrict__ coef, float* __restrict__ Aop, int64_t F) {
     __shared__ int s_parent[32];
     __shared__ int s_depth[32];
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 32) s_parent[threadIdx.x] = (threadIdx.x < NJ) ? parents[threadIdx.x] : -1;
@@ -367,7 +367,7 @@ joints_assemble_kernel(const float* __restrict__ J_posed, const float* __restric
                        float divisor, float* __restrict__ kp2d, const int32_t* __restrict__ gather,
                        int n_gather, float* __restrict__ gathered, int64_t F) {
     __shared__ float ex_s[JA_FB][JA_MAX_EXTRA * 3];
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
     const int64_t f0 = (int64_t)blockIdx.x * JA_FB;
     const int nf = (int)min((int64_t)JA_FB, F - f0);
@@ -450,7 +450,7 @@ __global__ void pack_theta_kernel(const float* __restrict__ R, const float* __re
 __global__ void smpl_reduced_joints_kernel(const float* __restrict__ A, const float* __restrict__ u, int64_t ldu,
                                            const float* __restrict__ lm_weights, const float* __restrict__ s,
                                            float* __restrict__ lm_out, float* __restrict__ thorax, int64_t F, int n_lm) {
-    pdl_wait();
+    pdl_wait_cta();
     pdl_trigger();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int per = n_lm + 1;
