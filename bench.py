@@ -347,6 +347,17 @@ def run_e2e(head, timer, args, feats_host, S, T, world):
 
 def lbs_roofline(head, args, F, peaks, stages):
     lbs_ms = head.time_stage_back_to_back("lbs", launches=8, repeats=5) if len(head._slots) >= 2 else stages["lbs"]["ms"]
+    # the product launches the kernel with programmatic dependent launch (its prologue runs under the previous kernel's tail,
+    # here under the previous launch of the same kernel); the same measurement with that switched off is reported beside it
+    from gaitb200 import _lib
+    lib = _lib.load()
+    mask = lib.gait_debug_pdl_mask(-1)
+    lib.gait_debug_pdl_mask(mask)
+    lbs_ms_serial = None
+    if len(head._slots) >= 2 and (mask & 2):
+        lib.gait_debug_pdl_mask(mask & ~2)
+        lbs_ms_serial = head.time_stage_back_to_back("lbs", launches=8, repeats=5)
+        lib.gait_debug_pdl_mask(mask)
     jo = not head.write_mesh
     lbs_bytes = F * (LBS_BYTES_PER_FRAME - (6890 * 3 * 4 - 21 * 12 if jo else 0)) + LBS_BYTES_ONCE
     lbs_gbs = lbs_bytes / (lbs_ms * 1e-3) / 1e9
@@ -360,8 +371,13 @@ def lbs_roofline(head, args, F, peaks, stages):
             "frac": lbs_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peaks["source"], "frames_per_launch": F, "algorithmic_bytes_per_launch": lbs_bytes, "kernel_ms": lbs_ms,
             "timing": ("8 consecutive launches between one CUDA-event pair on the launching stream, two alternating "
-                       "buffer sets (> 126 MB L2), best of 5") if len(head._slots) >= 2 else
+                       "buffer sets (> 126 MB L2), best of 5; launched as in the step, i.e. with programmatic dependent launch "
+                       "when GAITB200_PDL has bit 2 (default): consecutive launches overlap prologue and tail, so the average "
+                       "per launch is below the isolated kernel duration ncu reports (traffic_source)") if len(head._slots) >= 2 else
                       "one launch per CUDA-event pair after an L2 flush (one buffer slot)",
+            "pdl_mask": mask,
+            "kernel_ms_fully_serialised_launches": lbs_ms_serial,
+            "frac_fully_serialised_launches": (lbs_bytes / (lbs_ms_serial * 1e-3) / 1e9 / peaks["hbm_gbs"]) if lbs_ms_serial else None,
             "kernel_ms_single_launch_event_pair": stages["lbs"]["ms"],
             "frac_single_launch_event_pair": lbs_bytes / (stages["lbs"]["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"]}
 

@@ -50,6 +50,11 @@ const char* gait_error_string(int code);
 const char* gait_last_error(void);            /* thread-local detail of the last failure */
 /* sm count / compute capability of the current device; fails unless it is sm_100. */
 int gait_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* A/B hook: sets the mask of kernel kinds launched with programmatic dependent launch (1 tensor-core GEMM, 2 skinning,
+ * 4 small kernels; default 3, or GAITB200_PDL) and returns the previous mask; a negative value restores the default.
+ * Graphs captured earlier keep the edges they were captured with. */
+int gait_debug_pdl_mask(int mask);
+
 /* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t gait_launch_count(void);
 

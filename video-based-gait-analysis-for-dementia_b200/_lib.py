@@ -40,6 +40,7 @@ _SIGS = {
     "gait_linear_prepared": [P, I64, P, I64, P, I64, P, P, P, I64, P, I64, I64, I64, I64, P],
     "gait_debug_linear_trace": [P],
     "gait_debug_gru_trace": [P],
+    "gait_debug_pdl_mask": [I32],
     "gait_gru_workspace_bytes": [I64, I64, I64],
     "gait_gru_plan": [I64, I64, I64],
     "gait_gru_layer": [P, I64, P, P, P, P, P, P, I64, P, I64, P, I64, P, I64, I64, I64, I64, I32, P, SZ, P],

@@ -35,11 +35,13 @@ int device_sm_count() {
     return sms;
 }
 
+static std::atomic<int> g_pdl_mask{-1};
 int pdl_mask() {
-    static int on = -1;
+    int on = g_pdl_mask.load(std::memory_order_relaxed);
     if (on < 0) {
         const char* e = getenv("GAITB200_PDL");
         on = e ? atoi(e) : 3;
+        g_pdl_mask.store(on, std::memory_order_relaxed);
     }
     return on;
 }
@@ -78,6 +80,12 @@ int gait_device_info(int* sm_count, int* cc_major, int* cc_minor) {
         return GAIT_ERR_UNSUPPORTED;
     }
     return GAIT_OK;
+}
+
+int gait_debug_pdl_mask(int mask) {
+    const int prev = gait::pdl_mask();
+    gait::g_pdl_mask.store(mask, std::memory_order_relaxed);      // < 0: back to GAITB200_PDL / the default at the next launch
+    return prev;
 }
 
 int64_t gait_launch_count(void) { return gait::g_launches.load(std::memory_order_relaxed); }
