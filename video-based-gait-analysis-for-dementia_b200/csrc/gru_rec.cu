@@ -8,8 +8,9 @@
 //     h_{t-1} for all (<= 64) sequences, so per step a CTA streams 96 x H/2 weights (L2-resident: W_hh is read
 //     T times) and only 64 x H/2 of the hidden state.
 //   * operands: A = [h_hi ; h_lo] (64 + 64 rows) lives in TENSOR MEMORY (TMA loads h and h_lo - the latter written
-//     by the finalising threads of the previous step - and the converter warps move the rows with tcgen05.st;
-//     TS-mode MMAs read them), B = W_hi then W_lo (96 rows) in shared memory: two M128 N96 K8 MMAs per k-step
+//     by the finalising threads of the previous step - and one thread of warp 20 hands the landed tile to the tensor
+//     core's copy engine, tcgen05.cp shared -> tensor memory; until round 2 the converter warps moved the rows through
+//     their registers with tcgen05.st; TS-mode MMAs read them), B = W_hi then W_lo (96 rows) in shared memory: two M128 N96 K8 MMAs per k-step
 //     give h_hi.W + h_lo.W in TMEM lanes 0-63 / 64-127 (all four split products).  Split: hi = the raw FP32 word
 //     (the tensor core ignores the low 13 mantissa bits), lo = RN_tf32(x - trunc(x)), so only W_lo is ever
 //     written to shared memory by a thread (the first version was bound by the shared-memory pipe: LDS/STS +
@@ -25,7 +26,10 @@
 //     needs (relaxed loads + one acquire fence) before the TMA loads; the W tiles of the next step are prefetched
 //     while those flags are awaited.
 // Warp roles: 0 = W TMA producer, 1 and 3 = MMA issuers (even / odd accumulator chunks; 1 owns TMEM), 2 = h TMA producer (polls the flags),
-// 4-11 = promotion + gates (256 threads), 12-19 = converters (two groups of 4 warps alternating k-blocks).
+// 4-11 = promotion + gates (256 threads), 12-19 = W_lo converters (two groups of 4 warps alternating k-blocks), 20 = A-operand copier.
+// Registers are re-divided per warpgroup with setmaxnreg (40 / 120 / 56): the promotion warps hold a 48-float accumulator
+// tile next to the gate math (they spilled at the 96 registers a 672-thread kernel gets; gate phase 4.2k -> 1.7k cycles).
+// GRU_EXP_* macros are timing experiments (wrong results) kept for the measurements DESIGN.md section 4.2 quotes.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -57,7 +61,10 @@ constexpr int NBUF = 3;                     // TMEM accumulator ring (3 x 96 col
 constexpr int TMEM_A = NBUF * NB;           // A operand ring: STAGES x 32 columns, lanes 0-63 h_hi, 64-127 h_lo
 constexpr int TMEM_COLS = 512;
 static_assert(NBUF * NB + STAGES * BK <= 512, "tensor memory budget");
-constexpr int DRAIN_KB = 2;                 // k-blocks per promotion
+#ifndef GRU_DRAIN_KB
+#define GRU_DRAIN_KB 2
+#endif
+constexpr int DRAIN_KB = GRU_DRAIN_KB;      // k-blocks per promotion
 constexpr int NGRP = 2;                     // converter groups of 4 warps alternating k-blocks (a third group: 768 threads with
                                             // setmaxnreg, 0.475 vs 0.483 ms - not kept; it would also need its own barrier split)
 constexpr int NPROM = 256, NCONV = 128 * NGRP;
