@@ -185,6 +185,8 @@ class GaitHead(nn.Module):
         state = p["state"].data_ptr()
         betas, cam = state + 4 * 144, state + 4 * 154
         L.prepare_weight(gru.weight_ih_l0)
+        if T > 1 and L.load().gait_gru_plan(S, T, H) == 0:
+            L.prepare_weight(gru.weight_hh_l0)        # per-step recurrence (many sequences): T-1 GEMMs over W_hh per step
         fk = reg.fold(self.n_iter) if self.fold_regressor else None
         if "red_u" in p:
             # joints-only without the mesh: chain (plain transforms), one small GEMM, landmark skinning + thorax, assembly
