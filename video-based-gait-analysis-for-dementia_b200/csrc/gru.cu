@@ -48,6 +48,53 @@ __global__ void gru_gate_kernel(const float* __restrict__ gi, const float* __res
     if (hn) hn[(int64_t)s * H + u] = h;
 }
 
+// Same, four hidden units per thread with 128-bit accesses (H % 4 == 0, every base pointer 16-byte aligned and every row
+// stride a multiple of 4 floats): at 1024 sequences the scalar kernel took 25 us per step.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__global__ void gru_gate4_kernel(const float* __restrict__ gi, const float* __restrict__ gh, int gh_parts,
+                                 int64_t gh_part_stride, const float* __restrict__ b_hh, const float* __restrict__ hprev, int64_t ldh,
+                                 float* __restrict__ y, int64_t ldy, const float* __restrict__ resid, int64_t ldres,
+                                 float* __restrict__ out, int64_t ldout, float* __restrict__ hn, int S, int T,
+                                 int H, int t) {
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int s = blockIdx.y;
+    if (u >= H) return;
+    const int64_t f = (int64_t)s * T + t;
+    const float* g = gi + f * 3 * H;
+    float4 hr, hz, hnn;
+    if (gh) {
+        const float* q = gh + (int64_t)s * 3 * H;
+        hr = ld4(q + u); hz = ld4(q + H + u); hnn = ld4(q + 2 * H + u);
+        for (int part = 1; part < gh_parts; ++part) {
+            q += gh_part_stride;
+            const float4 a = ld4(q + u), b = ld4(q + H + u), c = ld4(q + 2 * H + u);
+            hr.x += a.x; hr.y += a.y; hr.z += a.z; hr.w += a.w;
+            hz.x += b.x; hz.y += b.y; hz.z += b.z; hz.w += b.w;
+            hnn.x += c.x; hnn.y += c.y; hnn.z += c.z; hnn.w += c.w;
+        }
+    } else {
+        hr = ld4(b_hh + u); hz = ld4(b_hh + H + u); hnn = ld4(b_hh + 2 * H + u);
+    }
+    const float4 hp = hprev ? ld4(hprev + (int64_t)s * ldh + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 gr = ld4(g + u), gz = ld4(g + H + u), gn = ld4(g + 2 * H + u);
+    float4 h;
+#define GAIT_GATE1(c)                                                  \
+    {                                                                  \
+        const float r = sigmoidf_(gr.c + hr.c);                        \
+        const float z = sigmoidf_(gz.c + hz.c);                        \
+        const float n = tanhf(gn.c + r * hnn.c);                       \
+        h.c = (1.f - z) * n + z * hp.c;                                \
+    }
+    GAIT_GATE1(x) GAIT_GATE1(y) GAIT_GATE1(z) GAIT_GATE1(w)
+#undef GAIT_GATE1
+    *reinterpret_cast<float4*>(y + f * ldy + u) = h;
+    if (out) {
+        const float4 rs = ld4(resid + f * ldres + u);
+        *reinterpret_cast<float4*>(out + f * ldout + u) = make_float4(h.x + rs.x, h.y + rs.y, h.z + rs.z, h.w + rs.w);
+    }
+    if (hn) *reinterpret_cast<float4*>(hn + (int64_t)s * H + u) = h;
+}
+
 __global__ void relu_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) y[i] = fmaxf(x[i], 0.f);
@@ -195,6 +242,14 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
             }
             ghp = gh;
         }
+        const bool vec4 = (H % 4 == 0) && aligned16(gi) && aligned16(gh) && aligned16(b_hh) && aligned16(y) && (ldy % 4 == 0) &&
+                          (!hprev || (aligned16(hprev) && ldh % 4 == 0)) &&
+                          (!out || (aligned16(out) && aligned16(resid) && ldout % 4 == 0 && ldres % 4 == 0)) && (!hn || aligned16(hn));
+        if (vec4) {
+            const dim3 grid4((unsigned)ceil_div(H / 4, 256), (unsigned)S);
+            gru_gate4_kernel<<<grid4, block, 0, st>>>(gi, ghp, parts, S * 3 * H, b_hh, hprev, ldh, y, ldy, resid, ldres, out, ldout,
+                                                      (step == T - 1) ? hn : nullptr, (int)S, (int)T, (int)H, (int)t);
+        } else
         gru_gate_kernel<<<grid, block, 0, st>>>(gi, ghp, parts, S * 3 * H, b_hh, hprev, ldh, y, ldy, resid, ldres, out, ldout,
                                                 (step == T - 1) ? hn : nullptr, (int)S, (int)T, (int)H, (int)t);
         GAIT_TRY(check_launch("gru_gate"));
