@@ -659,7 +659,16 @@ int linear_tc_launch(const float* A, int64_t lda, const float* W, int64_t ldw, c
             return launch<64, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
         return launch<128, false>(tmP, tmQ, tmQ, bias, Cin, ldcin, C, ldc, (int)N, (int)M, (int)K, 1, splits, split_stride, stream);
     }
-    const int bn = (ceil_div(M, BM) * ceil_div(N, 128) < 120 && N > 64) ? 64 : 128;
+    // tile width by a two-line cost model: waves of persistent CTAs x the measured k-block period of the tile shape (1300
+    // cycles for 128 x 128, 875 for 128 x 64).  256 x 6144 (a recurrence step for 256 sequences): 96 wide tiles
+    // in one wave beat 192 narrow ones in two (42 vs 57 us); 1024 x 1024 (regressor): 128 narrow tiles in one wave win.
+    int bn = 128;
+    if (N > 64) {
+        const int64_t sms = device_sm_count(), rt = ceil_div(M, BM);
+        const int64_t cost128 = ceil_div(rt * ceil_div(N, 128) * splits, sms) * 1300;
+        const int64_t cost64 = ceil_div(rt * ceil_div(N, 64) * splits, sms) * 875;
+        if (cost64 < cost128) bn = 64;
+    }
     GAIT_TRY(make_map(&tmP, A, M, K, lda, P_BOX));
     const float *Whi = nullptr, *Wlo = nullptr;
     if (find_prepared(W, (N - 1) * ldw + K, &Whi, &Wlo) && aligned16(Whi) && aligned16(Wlo)) {
