@@ -149,8 +149,10 @@ def test_prepared_weight_matches_unprepared(lib_loaded):
     dict(S=5, T=9, I=96, H=256, layers=2, bi=True),           # persistent kernel: ragged S, reverse direction, ldy = 2H
     dict(S=64, T=4, I=40, H=64, layers=1, bi=False),          # persistent kernel: one k-block per CTA
     dict(S=37, T=1, I=64, H=128, layers=1, bi=False),         # single step: no recurrent GEMM at all
-    dict(S=70, T=5, I=64, H=128, layers=1, bi=False),         # 64 < S < 128: two launches of the persistent kernel (64 + 6 sequences)
-    dict(S=200, T=3, I=64, H=128, layers=1, bi=False),        # S >= 128: per-step path
+    dict(S=70, T=5, I=64, H=128, layers=1, bi=False),         # small layer, 64 < S <= 320: two launches of the persistent kernel (64 + 6 sequences)
+    dict(S=200, T=3, I=64, H=128, layers=1, bi=False),        # small layer, four launches of the persistent kernel
+    dict(S=330, T=3, I=64, H=128, layers=1, bi=False),        # small layer beyond 320 sequences: per-step path
+    dict(S=70, T=3, I=64, H=1024, layers=1, bi=False),        # large layer (H >= 1024) beyond 64 sequences: per-step path, W_hh prepared
 ])
 def test_gru_vs_torch(cfg, lib_loaded):
     from gaitb200.temporal import gru_forward
@@ -201,8 +203,9 @@ def test_gru_plan_selects_the_fast_kernels(lib_loaded):
         pytest.skip("GRU path overridden by the environment")
     plan = lib_loaded.load().gait_gru_plan
     assert plan(64, 16, 2048) == 1          # C2: persistent cluster kernel
-    assert plan(100, 16, 2048) == 1         # 65 ... 127 sequences: two 64-sequence launches of the persistent kernel
-    assert plan(128, 16, 2048) == 0         # C3 at 8 GPUs: per-step GEMMs (measured faster from 128 sequences on)
+    assert plan(100, 16, 2048) == 0         # more than one 64-sequence launch at H = 2048: per-step GEMMs (measured faster)
+    assert plan(128, 16, 2048) == 0         # C3 at 8 GPUs
+    assert plan(100, 16, 128) == 1          # small layers keep the multi-launch persistent path
     assert plan(1, 900, 2048) == 2          # C4: weight-stationary kernel
     assert plan(1024, 16, 2048) == 0        # C3 on one GPU: per-step GEMMs
     assert plan(4, 6, 300) == 0             # H not a multiple of 64

@@ -127,7 +127,7 @@ int gait_gru_plan(int64_t S, int64_t T, int64_t H) {
     const char* sm = getenv("GAITB200_GRU_SMALL");
     if (!(sm && atoi(sm) == 0) && T >= 4 && gru_small_eligible(a, a, nullptr, a, H, S, T, H)) return 2;
     const char* mc = getenv("GAITB200_GRU_MAXCHUNKED");
-    const int64_t max_chunked = mc ? atoll(mc) : 127;
+    const int64_t max_chunked = mc ? std::max<int64_t>(0, atoll(mc)) : (H >= 1024 ? 64 : 320);
     if (S <= max_chunked && gru_recurrent_eligible(a, a, nullptr, a, H, a, H, a, H, std::min<int64_t>(S, 64), T, H)) return 1;
     return 0;
 }
@@ -178,21 +178,24 @@ int gait_gru_layer(const float* x, int64_t ldx, const float* W_ih, const float* 
         if (rc != GAIT_GRU_RETRY_PER_STEP) return rc;
     }
     if (gru_path != 1 && linear_path() != 1) {
-        // up to 127 sequences run as consecutive 64-sequence launches of the persistent kernel (beyond that the per-step
-        // GEMMs, whose efficiency grows with the number of rows, win)
+        // consecutive 64-sequence launches of the persistent kernel (kept for small layers and as an A/B switch; at H = 2048 the
+        // per-step GEMMs, whose efficiency grows with the number of rows, win as soon as there is more than one launch)
         constexpr int64_t kChunk = 64;
         // crossover measured on B200 (scripts/gru_s_sweep.py, profiles/r02zf_gru_s_sweep.md): GRU stage M frames/s at
         // S = 64/128/192/256/320/512: 64-sequence chunks 2.27/2.37/2.46/2.45/2.49/2.44, per-step 2.08/2.71/2.50/3.03/3.50/3.23
         // (per-step path with W_hh prepared, the vectorised gate kernel and the tile-width cost model of linear_tc.cu; before
-        // those it won only from 512 sequences on).  Below 128 rows the per-step GEMM runs in its transposed form: not measured,
-        // the chunked persistent kernel keeps 65 ... 127 sequences.
-        static int64_t kMaxChunked = -1;              // GAITB200_GRU_MAXCHUNKED: A/B switch for the crossover
-        if (kMaxChunked < 0) {
+        // those it won only from 512 sequences on); 72 / 96 / 112 sequences: chunks 1.53 / 1.95 / 2.17, per-step 1.95 / 2.40 / 2.64.
+        // So one launch of the persistent kernel for up to 64 sequences, the per-step path beyond.
+        static int64_t kMaxChunked = -2;              // GAITB200_GRU_MAXCHUNKED: A/B switch for the crossover (-1: not set)
+        if (kMaxChunked == -2) {
             const char* e = getenv("GAITB200_GRU_MAXCHUNKED");
-            kMaxChunked = e ? atoll(e) : 127;
+            kMaxChunked = e ? std::max<int64_t>(0, atoll(e)) : -1;
         }
+        // not set = by H: the crossover was measured at H = 2048 only (above); small layers, whose per-step GEMMs are
+        // launch-bound, keep the multi-launch persistent path up to 320 sequences
+        const int64_t max_chunked = kMaxChunked >= 0 ? kMaxChunked : (H >= 1024 ? 64 : 320);
         const int64_t S0 = std::min<int64_t>(S, kChunk);
-        if (S <= kMaxChunked && gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S0, T, H)) {
+        if (S <= max_chunked && gru_recurrent_eligible(gi, W_hh, h0, y, ldy, resid, ldres, out, ldout, S0, T, H)) {
             unsigned int* counter = reinterpret_cast<unsigned int*>(gh + kGruMaxSplits * S * 3 * H);
             uintptr_t lo_addr = (reinterpret_cast<uintptr_t>(counter) + 128 * (size_t)(H / 16 + 1) + 127) & ~(uintptr_t)127;
             bool refused = false;
