@@ -44,6 +44,34 @@ def test_library_is_sm100a_only(lib):
     assert archs == {"100a"}, archs
 
 
+def test_kernels_use_the_blackwell_instructions_design_md_names(lib):
+    """SASS of the built library: the hot kernels really are tcgen05 / tensor-memory / TMA code with per-role register
+    budgets and programmatic dependent launch (mnemonics as in /opt/skills/guides/B200_PROFILING.md)."""
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    kernels = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            kernels[cur] = set()
+        elif cur is not None:
+            for mn in ("UTCHMMA", "UTCCP", "LDTM", "STTM", "UTMALDG", "UBLKCP", "USETMAXREG", "ACQBULK"):
+                if mn in line:
+                    kernels[cur].add(mn)
+
+    def has(name_part, *mns):
+        hits = [k for k in kernels if name_part in k]
+        assert hits, name_part
+        for k in hits:
+            assert set(mns) <= kernels[k], (k, sorted(kernels[k]))
+
+    has("gemm_tf32x3_kernel", "UTCHMMA", "LDTM", "STTM", "UTMALDG", "USETMAXREG", "ACQBULK")      # tcgen05.mma, TMEM ld/st, TMA, setmaxnreg, griddepcontrol.wait
+    has("gru_recurrent_kernel", "UTCHMMA", "UTCCP", "LDTM", "UTMALDG", "USETMAXREG")               # + tcgen05.cp
+    has("smpl_lbs_tc_kernel", "UTCHMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "USETMAXREG", "ACQBULK")
+    has("joint_regress_stream_kernel", "UBLKCP")
+
+
 def test_version_and_error_strings(lib):
     assert lib.gait_abi_version() == 1
     assert lib.gait_error_string(0) == b"ok"
